@@ -1,0 +1,146 @@
+"""ctypes binding of libdsk.so (the C ABI in include/dsk.h) and the in-tree nvcc build recipe.
+
+The product path has no fallback: if the shared library is missing or an entry point fails, a
+RuntimeError is raised (north star: "no CPU fallback, no multi-backend dispatch").
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libdsk.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+NUM_CONV = 12
+DSK_F16, DSK_BF16 = 0, 1
+DSK_EVAL, DSK_TRAIN = 0, 1
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + [
+        os.path.join(INCLUDE, "dsk.h")
+    ]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into lib/libdsk.so (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libdsk.so")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        "-o", LIB_PATH, os.path.join(CSRC, "dsk_api.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+class DskWeights(ctypes.Structure):
+    _fields_ = [
+        ("conv_w", c_void_p * NUM_CONV),
+        ("bn_gamma", c_void_p * NUM_CONV),
+        ("bn_beta", c_void_p * NUM_CONV),
+        ("bn_running_mean", c_void_p * NUM_CONV),
+        ("bn_running_var", c_void_p * NUM_CONV),
+        ("fc_w", c_void_p),
+        ("fc_b", c_void_p),
+        ("embedding_size", c_int32),
+    ]
+
+
+class DskGrads(ctypes.Structure):
+    _fields_ = [
+        ("conv_w", c_void_p * NUM_CONV),
+        ("bn_gamma", c_void_p * NUM_CONV),
+        ("bn_beta", c_void_p * NUM_CONV),
+        ("fc_w", c_void_p),
+        ("fc_b", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/dsk.h
+SIGNATURES = {
+    "dsk_last_error": (c_char_p, []),
+    "dsk_version": (c_int32, []),
+    "dsk_create": (c_int32, [POINTER(c_void_p), c_int32, c_int32]),
+    "dsk_destroy": (c_int32, [c_void_p]),
+    "dsk_load_weights": (c_int32, [c_void_p, POINTER(DskWeights), c_void_p]),
+    "dsk_rescnn_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "dsk_conv2d_nhwc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                  c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "dsk_pack_conv_weight": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "dsk_nchw_f32_to_nhwc16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "dsk_nhwc16_to_nchw_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "dsk_pairwise_distance": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "dsk_pairwise_distance_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                            c_void_p, c_void_p]),
+    "dsk_triplet_loss": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    "dsk_triplet_loss_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                       c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dsk_margin_select": (c_int32, [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
+    "dsk_gather_rows": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+    "dsk_allpairs_topk": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libdsk.so (building it first if sources are newer). Raises if unavailable — no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if needs_build():
+        try:
+            build()
+        except Exception as e:  # a GPU box without nvcc must ship the prebuilt .so
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(f"libdsk.so is missing and could not be built: {e}") from e
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().dsk_last_error()
+        raise RuntimeError(f"libdsk {what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def cur_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int:
+    """Raw device pointer of a tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()

@@ -1,0 +1,216 @@
+// CUDA-core kernels around the tensor-core convs: weight repack, BN folding, the Cin=1 first conv,
+// temporal mean-pool + fc + L2-norm tail.  NHWC 16-bit activations (fp16 or bf16 via template).
+#pragma once
+#include "dsk_ptx.cuh"
+
+namespace dsk {
+
+// ---------------------------------------------------------------------------------------------
+// OIHW fp32 -> [tap][cout][cin] 16-bit (tap = r*S + s). One-time at weight load.
+// ---------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int cout, int cin,
+                                        int taps) {
+  const long total = static_cast<long>(cout) * cin * taps;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ci = i % cin;
+    const long r = i / cin;
+    const int co = r % cout;
+    const int tap = r / cout;
+    out[i] = to16<BF16>(w[(static_cast<long>(co) * cin + ci) * taps + tap]);
+  }
+}
+
+// Same but with the filter rotated by 180 degrees and cin/cout swapped: the weight of the
+// "data-gradient as a convolution" of a stride-1 conv. out[tap'][ci][co] = w[co][ci][taps-1-tap'].
+template <bool BF16>
+__global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int cout,
+                                              int cin, int taps) {
+  const long total = static_cast<long>(cout) * cin * taps;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int co = i % cout;
+    const long r = i / cout;
+    const int ci = r % cin;
+    const int tap = r / cin;
+    out[i] = to16<BF16>(w[(static_cast<long>(co) * cin + ci) * taps + (taps - 1 - tap)]);
+  }
+}
+
+// Eval-mode BatchNorm folded to y = x*scale + bias  (/root/reference/model.py:59,62,94,99,103,107;
+// torch defaults eps=1e-5).
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                               float* __restrict__ scale, float* __restrict__ bias, int c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) {
+    const float s = gamma[i] / sqrtf(var[i] + eps);
+    scale[i] = s;
+    bias[i] = beta[i] - mean[i] * s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1: 5x5 s2 p2, Cin=1 -> 64 (/root/reference/model.py:93, used at :187), + affine (+clip).
+// x fp32 (B, T, 64) [= NCHW with C=1]; out NHWC 16-bit (B, T/2, 32, 64).
+// Block = 4 output rows of one utterance; warp = 16 pixels; lane = 2 output channels, whose
+// 50 filter weights live in registers; the input patch is broadcast from shared memory.
+// ---------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]*/, const float* __restrict__ scale,
+             const float* __restrict__ bias, uint16_t* __restrict__ out, int T, int do_clip, float clip_hi) {
+  constexpr int WIN = 64, WOUT = 32, ROWS = 4, PATCH_ROWS = 2 * ROWS + 3, PATCH_W = WIN + 4;
+  __shared__ float patch[PATCH_ROWS][PATCH_W];
+  const int hout = T / 2;
+  const int tiles_h = (hout + ROWS - 1) / ROWS;
+  const int n = blockIdx.x / tiles_h;
+  const int h0 = (blockIdx.x % tiles_h) * ROWS;
+  const float* xin = x + static_cast<long>(n) * T * WIN;
+  for (int i = threadIdx.x; i < PATCH_ROWS * PATCH_W; i += blockDim.x) {
+    const int pr = i / PATCH_W, pc = i % PATCH_W;
+    const int ih = 2 * h0 - 2 + pr, iw = pc - 2;
+    patch[pr][pc] = (ih >= 0 && ih < T && iw >= 0 && iw < WIN) ? xin[ih * WIN + iw] : 0.0f;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = lane * 2;
+  float w0[25], w1[25];
+#pragma unroll
+  for (int t = 0; t < 25; ++t) {
+    w0[t] = w[c0 * 25 + t];
+    w1[t] = w[(c0 + 1) * 25 + t];
+  }
+  const float s0 = scale[c0], s1 = scale[c0 + 1], b0 = bias[c0], b1 = bias[c0 + 1];
+  __syncthreads();
+  uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+  for (int pi = 0; pi < 16; ++pi) {
+    const int p = warp * 16 + pi;  // 0..127 = 4 rows x 32 cols
+    const int lh = p >> 5, ow = p & 31;
+    const int oh = h0 + lh;
+    if (oh >= hout) break;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        const float v = patch[2 * lh + r][2 * ow + s];
+        a0 = fmaf(v, w0[r * 5 + s], a0);
+        a1 = fmaf(v, w1[r * 5 + s], a1);
+      }
+    }
+    a0 = fmaf(a0, s0, b0);
+    a1 = fmaf(a1, s1, b1);
+    if (do_clip) {
+      a0 = fminf(fmaxf(a0, 0.f), clip_hi);
+      a1 = fminf(fmaxf(a1, 0.f), clip_hi);
+    }
+    const long pix = (static_cast<long>(n) * hout + oh) * WOUT + ow;
+    o32[pix * 32 + lane] = pack2<BF16>(a0, a1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tail: temporal mean (/root/reference/model.py:111,207-208) -> fc (:164,209) -> l2_norm*alpha
+// (:172-183,210-213).
+// pooled[b][w*C + c] = mean_h act[b][h][w][c]   (act NHWC 16-bit, W=4, C=512)
+// The fc weight is repacked once to the same (w, c) column order: wq[e][w*C + c] = W[e][c*4 + w].
+// ---------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void pool_time_kernel(const uint16_t* __restrict__ act, float* __restrict__ pooled, int H, int WC) {
+  // grid (B), block 256; each thread 2 adjacent elements per step (32-bit loads)
+  const int b = blockIdx.x;
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(act + static_cast<long>(b) * H * WC);
+  const float inv = 1.0f / static_cast<float>(H);
+  for (int i = threadIdx.x; i < WC / 2; i += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int h = 0; h < H; ++h) {
+      const float2 v = unpack2<BF16>(a[h * (WC / 2) + i]);
+      s0 += v.x;
+      s1 += v.y;
+    }
+    pooled[static_cast<long>(b) * WC + 2 * i] = s0 * inv;
+    pooled[static_cast<long>(b) * WC + 2 * i + 1] = s1 * inv;
+  }
+}
+
+__global__ void pack_fc_weight_kernel(const float* __restrict__ w /*[E][C*4+w]*/, float* __restrict__ out, int E,
+                                      int C, int W) {
+  const long total = static_cast<long>(E) * C * W;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = i % C;
+    const long r = i / C;
+    const int wi = r % W;
+    const int e = r / W;
+    out[i] = w[(static_cast<long>(e) * C + c) * W + wi];
+  }
+}
+
+// y[b][e] = sum_k pooled[b][k] * wq[e][k] + bias[e].  grid (ceil(B/8), E/64), block 256.
+__global__ void __launch_bounds__(256)
+fc_kernel(const float* __restrict__ pooled, const float* __restrict__ wq, const float* __restrict__ bias,
+          float* __restrict__ y, int B, int K, int E) {
+  constexpr int UT = 8;
+  extern __shared__ float sp[];  // [UT][K]
+  const int b0 = blockIdx.x * UT;
+  const int e0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < UT * K; i += blockDim.x) {
+    const int u = i / K;
+    sp[i] = (b0 + u < B) ? pooled[static_cast<long>(b0 + u) * K + (i - u * K)] : 0.f;
+  }
+  __syncthreads();
+  const int e = e0 + (threadIdx.x >> 2);
+  const int part = threadIdx.x & 3;
+  const float4* wr = reinterpret_cast<const float4*>(wq + static_cast<long>(e) * K);
+  float acc[UT];
+#pragma unroll
+  for (int u = 0; u < UT; ++u) acc[u] = 0.f;
+  for (int i = part; i < K / 4; i += 4) {
+    const float4 wv = wr[i];
+#pragma unroll
+    for (int u = 0; u < UT; ++u) {
+      const float4 pv = reinterpret_cast<const float4*>(sp + u * K)[i];
+      acc[u] = fmaf(wv.x, pv.x, acc[u]);
+      acc[u] = fmaf(wv.y, pv.y, acc[u]);
+      acc[u] = fmaf(wv.z, pv.z, acc[u]);
+      acc[u] = fmaf(wv.w, pv.w, acc[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UT; ++u) {
+    acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], 1);
+    acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], 2);
+  }
+  if (part == 0) {
+    const float bb = bias[e];
+#pragma unroll
+    for (int u = 0; u < UT; ++u)
+      if (b0 + u < B) y[static_cast<long>(b0 + u) * E + e] = acc[u] + bb;
+  }
+}
+
+// out[b][:] = alpha * y[b][:] / sqrt(sum(y^2) + 1e-10)   (/root/reference/model.py:172-183,210-213)
+// also writes inv_norm[b] = 1/sqrt(sum+1e-10) when inv_norm != nullptr (saved for backward).
+__global__ void l2norm_kernel(const float* __restrict__ y, float* __restrict__ out, float* __restrict__ inv_norm,
+                              int E, float alpha) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* yr = y + static_cast<long>(b) * E;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) s = fmaf(yr[i], yr[i], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float norm = sqrtf(red[0] + 1e-10f);
+  if (threadIdx.x == 0 && inv_norm) inv_norm[b] = 1.0f / norm;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) out[static_cast<long>(b) * E + i] = (yr[i] / norm) * alpha;
+}
+
+}  // namespace dsk

@@ -1,0 +1,136 @@
+/*
+ * dsk.h — C ABI of the B200-native Deep Speaker hot path (libdsk.so).
+ *
+ * The reference (qqueing/DeepSpeaker-pytorch) is 100 % Python and reaches the GPU only through
+ * torch.nn library calls; it has no FFI of its own.  Each entry point below therefore cites the
+ * reference *Python* call site whose arithmetic it replaces (file:line in /root/reference).
+ * A maintainer binds these with ctypes; the host-side mirror of the
+ * reference's classes lives in deepspeaker_pytorch_b200/model.py.
+ *
+ * Conventions
+ *  - every pointer is a raw CUDA device pointer owned by the caller (PyTorch); the library
+ *    borrows it for the duration of the call and never frees it;
+ *  - every function is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *    synchronises the device and never reads results on the host;
+ *  - return value: 0 on success, negative dsk_status on error; dsk_last_error() gives the
+ *    message of the last failure on the calling thread;
+ *  - no exceptions cross this boundary, there is no CPU fallback.
+ */
+#ifndef DSK_H_
+#define DSK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  DSK_OK = 0,
+  DSK_ERR_INVALID = -1, /* bad argument / unsupported shape */
+  DSK_ERR_CUDA = -2,    /* a CUDA runtime / driver call failed */
+  DSK_ERR_STATE = -3,   /* call sequence error (e.g. forward before load_weights) */
+  DSK_ERR_ARCH = -4     /* device is not sm_100 */
+} dsk_status;
+
+/* 16-bit tensor-core operand format (fp32 accumulation either way) */
+typedef enum { DSK_F16 = 0, DSK_BF16 = 1 } dsk_operand_t;
+
+/* BatchNorm behaviour of a forward: running statistics (eval) or batch statistics (train) */
+typedef enum { DSK_EVAL = 0, DSK_TRAIN = 1 } dsk_mode_t;
+
+#define DSK_NUM_CONV 12 /* conv1, layer1.0.conv1, layer1.0.conv2, conv2, layer2.0.conv1, ... layer4.0.conv2 */
+
+/* Parameters of DeepSpeakerModel.model (fp32, PyTorch layouts), /root/reference/model.py:91-112,162-164.
+ * conv_w[i]: OIHW.  i = 3*stage + {0: convK (5x5 s2), 1: layerK.0.conv1, 2: layerK.0.conv2 (3x3)}.
+ * bn_*[i]  : the BatchNorm2d that follows conv i (bnK, layerK.0.bn1, layerK.0.bn2).
+ * fc_w     : (embedding_size, 2048) with column index c*4 + w (model.py:164,208-209). */
+typedef struct {
+  const float* conv_w[DSK_NUM_CONV];
+  const float* bn_gamma[DSK_NUM_CONV];
+  const float* bn_beta[DSK_NUM_CONV];
+  float* bn_running_mean[DSK_NUM_CONV]; /* read in eval; updated in place in train (momentum 0.1) */
+  float* bn_running_var[DSK_NUM_CONV];
+  const float* fc_w;
+  const float* fc_b;
+  int32_t embedding_size; /* 512 */
+} dsk_weights;
+
+/* Gradients, same layouts as dsk_weights (fp32, written not accumulated). */
+typedef struct {
+  float* conv_w[DSK_NUM_CONV];
+  float* bn_gamma[DSK_NUM_CONV];
+  float* bn_beta[DSK_NUM_CONV];
+  float* fc_w;
+  float* fc_b;
+} dsk_grads;
+
+typedef struct dsk_handle_s* dsk_handle;
+
+const char* dsk_last_error(void);
+int32_t dsk_version(void);
+
+/* Per-module engine state (repacked weights, folded BN, workspace, TMA descriptors).
+ * Created at DeepSpeakerModel.cuda()/first call, released in __del__ (model.py:153-167). */
+int32_t dsk_create(dsk_handle* out, int32_t device, int32_t operand /* dsk_operand_t */);
+int32_t dsk_destroy(dsk_handle h);
+
+/* Repack conv weights to [tap][cout][cin] 16-bit, fold eval BatchNorm to scale/bias, reorder fc.
+ * Must be called after every parameter update (the Python shim tracks parameter versions). */
+int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream);
+
+/* DeepSpeakerModel.forward (/root/reference/model.py:185-218), BN in eval mode
+ * (train_triplet.py:332,347): x (B,1,T,64) fp32 contiguous -> emb (B,E) fp32 with ||emb||=10.
+ * T must be a multiple of 16. */
+int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, int32_t mode,
+                           void* stream);
+
+/* One fused conv layer on NHWC 16-bit tensors: out = clip(conv(in, w)*scale + bias (+res)).
+ * Building block of dsk_rescnn_forward, exported for unit tests against F.conv2d.
+ * ksize/stride in {(3,1),(5,2)}; cin, cout multiples of 64; flags: 1 = add residual, 2 = clip to [0,clip_hi].
+ * w_packed comes from dsk_pack_conv_weight. */
+int32_t dsk_conv2d_nhwc(dsk_handle h, const void* in, const void* w_packed, const float* scale, const float* bias,
+                        const void* res, void* out, int32_t B, int32_t Hin, int32_t Win, int32_t cin, int32_t cout,
+                        int32_t ksize, int32_t stride, int32_t flags, float clip_hi, void* stream);
+int32_t dsk_pack_conv_weight(dsk_handle h, const float* w_oihw, void* w_packed, int32_t cout, int32_t cin,
+                             int32_t ksize, void* stream);
+/* fp32 NCHW <-> 16-bit NHWC converters (test helpers; also used at the boundary for C>1 inputs) */
+int32_t dsk_nchw_f32_to_nhwc16(dsk_handle h, const float* in, void* out, int32_t B, int32_t C, int32_t H, int32_t W,
+                               void* stream);
+int32_t dsk_nhwc16_to_nchw_f32(dsk_handle h, const void* in, float* out, int32_t B, int32_t C, int32_t H, int32_t W,
+                               void* stream);
+
+/* PairwiseDistance(p=2).forward (/root/reference/model.py:8-18): out[i] = sqrt(sum_j (x1-x2)^2 + 1e-4/D). */
+int32_t dsk_pairwise_distance(const float* x1, const float* x2, int32_t B, int32_t D, float* out, void* stream);
+/* d(out)/d(x1) and d(out)/d(x2) given grad_out (B,), dist (B,) from the forward. Either grad pointer may be NULL. */
+int32_t dsk_pairwise_distance_bwd(const float* x1, const float* x2, const float* dist, const float* grad_out,
+                                  int32_t B, int32_t D, float* grad_x1, float* grad_x2, void* stream);
+
+/* TripletMarginLoss(margin).forward (/root/reference/model.py:19-33):
+ * loss = mean(clamp(margin + d_p - d_n, 0)). Writes loss (1,), d_p (B,), d_n (B,). */
+int32_t dsk_triplet_loss(const float* a, const float* p, const float* n, int32_t B, int32_t D, float margin,
+                         float* loss, float* d_p, float* d_n, void* stream);
+/* Gradients of the loss w.r.t. a, p, n scaled by grad_loss (device scalar). */
+int32_t dsk_triplet_loss_bwd(const float* a, const float* p, const float* n, const float* d_p, const float* d_n,
+                             const float* grad_loss, int32_t B, int32_t D, float margin, float* ga, float* gp,
+                             float* gn, void* stream);
+
+/* "Choose the hard negatives" (/root/reference/train_triplet.py:251-262):
+ * idx = ascending indices i with d_n[i] - d_p[i] < margin  (== np.where(mask == 1)); count on device. */
+int32_t dsk_margin_select(const float* d_p, const float* d_n, int32_t B, float margin, int64_t* idx,
+                          int32_t* count, void* stream);
+/* Row gather out[j] = src[idx[j]] for j < *count (train_triplet.py:265-274), row = row_elems fp32. */
+int32_t dsk_gather_rows(const float* src, const int64_t* idx, const int32_t* count, int32_t max_rows,
+                        int64_t row_elems, float* out, void* stream);
+
+/* All-pairs distance + per-row k smallest over different-label columns (BASELINE config 4; no reference
+ * implementation exists — defined from PairwiseDistance, model.py:13-18):
+ * D[i][j] = sqrt(sum_d (E[i]-E[j])^2 + 1e-4/Dim), candidates j with labels[j] != labels[i];
+ * ties broken by lower j. Writes idx (N,k) int64 and val (N,k) fp32, ascending distance. */
+int32_t dsk_allpairs_topk(const float* E, const int64_t* labels, int32_t N, int32_t D, int32_t k, int64_t* idx,
+                          float* val, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSK_H_ */
