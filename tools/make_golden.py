@@ -1,0 +1,141 @@
+"""Generate tests/golden/*.npz from the REFERENCE ITSELF (/root/reference/model.py, imported unmodified).
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tools/make_golden.py
+The fixtures pin oracle/rescnn_oracle.py (tests/test_oracle_golden.py) and, through it, the CUDA path.
+Inputs and parameters are regenerated from seeds by oracle.make_state_dict / make_input, so only
+outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+import model as R  # noqa: E402  (the reference's model.py)
+
+from oracle import rescnn_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+NUM_CLASSES = 16
+MARGIN = 0.1
+
+
+def sample_idx(numel, n=16, seed=123):
+    g = np.random.RandomState(seed)
+    return g.randint(0, numel, size=n).astype(np.int64)
+
+
+def ref_model(sd):
+    m = R.DeepSpeakerModel(512, NUM_CLASSES)
+    m.load_state_dict(sd)
+    return m
+
+
+def golden_eval():
+    sd = O.make_state_dict(0, NUM_CLASSES)
+    m = ref_model(sd).eval()
+    out = {}
+    for name, (B, T, seed, scale) in {"a": (4, 160, 0, 1.0), "b": (3, 32, 1, 10.0), "c": (2, 160, 2, 10.0)}.items():
+        x = O.make_input(B, T, seed, scale)
+        taps = {}
+        hooks = []
+        for s in range(4):
+            hooks.append(getattr(m.model, f"layer{s + 1}").register_forward_hook(
+                lambda mod, i, o, s=s: taps.__setitem__(3 * s + 2, o.detach().clone())))
+        with torch.no_grad():
+            e = m(x)
+        for hk in hooks:
+            hk.remove()
+        out[f"{name}_cfg"] = np.array([B, T, seed, scale], dtype=np.float64)
+        out[f"{name}_emb"] = e.numpy()
+        for k, v in taps.items():
+            flat = v.flatten()
+            ix = sample_idx(flat.numel())
+            out[f"{name}_tap{k}_idx"] = ix
+            out[f"{name}_tap{k}_val"] = flat[ix].numpy()
+            out[f"{name}_tap{k}_mean"] = np.array([flat.mean().item(), flat.abs().max().item()])
+    np.savez(os.path.join(OUT, "eval_forward.npz"), **out)
+    print("eval_forward.npz", {k: v.shape for k, v in out.items() if k.endswith("_emb")})
+
+
+def make_triplet_embeddings(B=64, D=512, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    nrm = lambda t: 10.0 * t / t.norm(dim=1, keepdim=True)
+    a = nrm(torch.randn(B, D, generator=g))
+    p = nrm(a + 0.25 * torch.randn(B, D, generator=g))
+    sig = torch.linspace(0.18, 0.34, B).view(B, 1)[torch.randperm(B, generator=g)]
+    n = nrm(a + sig * torch.randn(B, D, generator=g))
+    return a, p, n
+
+
+def golden_loss():
+    a, p, n = make_triplet_embeddings()
+    pd = R.PairwiseDistance(2)
+    d_p = pd.forward(a, p)                                   # train_triplet.py:251
+    d_n = pd.forward(a, n)                                   # :252
+    allm = (d_n - d_p < MARGIN).cpu().data.numpy().flatten()  # :253
+    hard = np.where(allm == 1)[0]                            # :262
+    loss = R.TripletMarginLoss(MARGIN).forward(a, p, n)      # :219
+    # gradients of the loss w.r.t. the embeddings (autograd through the reference's own forward)
+    a2, p2, n2 = (t.clone().requires_grad_(True) for t in (a, p, n))
+    R.TripletMarginLoss(MARGIN).forward(a2, p2, n2).backward()
+    sel_loss = R.TripletMarginLoss(MARGIN).forward(a[hard], p[hard], n[hard])   # :275 on the selected rows
+    np.savez(os.path.join(OUT, "triplet_loss.npz"), seed=np.array([64, 512, 5]), d_p=d_p.numpy(), d_n=d_n.numpy(),
+             hard_idx=hard.astype(np.int64), loss=np.array(loss.item(), dtype=np.float32),
+             selected_loss=np.array(sel_loss.item(), dtype=np.float32), ga=a2.grad.numpy(), gp=p2.grad.numpy(),
+             gn=n2.grad.numpy())
+    print("triplet_loss.npz: selected", len(hard), "of", len(allm), "loss", loss.item())
+
+
+def golden_train():
+    """Branch-A step (train_triplet.py:215-224) with the reference model in train mode."""
+    sd = O.make_state_dict(0, NUM_CLASSES)
+    m = ref_model(sd).train()
+    B, T = 4, 160
+    xa, xp, xn = (O.make_input(B, T, s, 3.0) for s in (10, 11, 12))
+    out_a, out_p, out_n = m(xa), m(xp), m(xn)                 # :215
+    loss = R.TripletMarginLoss(MARGIN).forward(out_a, out_p, out_n)   # :219
+    m.zero_grad()
+    loss.backward()                                           # :223
+    out = {"cfg": np.array([B, T, 10, 11, 12, 3.0]), "loss": np.array(loss.item(), dtype=np.float32),
+           "out_a": out_a.detach().numpy(), "out_p": out_p.detach().numpy(), "out_n": out_n.detach().numpy()}
+    for k, v in m.named_parameters():
+        if v.grad is None:
+            continue
+        gflat = v.grad.flatten()
+        ix = sample_idx(gflat.numel(), 32)
+        out["gnorm/" + k] = np.array(gflat.double().norm().item())
+        out["gidx/" + k] = ix
+        out["gval/" + k] = gflat[ix].numpy()
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            out["stat/" + k] = v.numpy()
+    np.savez(os.path.join(OUT, "train_step.npz"), **out)
+    print("train_step.npz: loss", loss.item(), "params with grad", sum(1 for k in out if k.startswith("gnorm/")))
+
+
+def golden_allpairs():
+    """Config 4 has no reference implementation: the fixture only pins the distance
+    formula on pairs, computed with the reference's PairwiseDistance."""
+    g = torch.Generator().manual_seed(3)
+    N, D = 96, 512
+    E = torch.randn(N, D, generator=g)
+    E = 10.0 * E / E.norm(dim=1, keepdim=True)
+    labels = (torch.arange(N) // 6).long()
+    pd = R.PairwiseDistance(2)
+    Dm = torch.stack([pd.forward(E[i:i + 1].expand(N, D), E) for i in range(N)])
+    np.savez(os.path.join(OUT, "allpairs.npz"), seed=np.array([N, D, 3]), dist=Dm.numpy(), labels=labels.numpy())
+    print("allpairs.npz", Dm.shape)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    golden_eval()
+    golden_loss()
+    golden_train()
+    golden_allpairs()
