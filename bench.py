@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — speaker-embeddings/sec of the ResCNN hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm, one B200
+    torchrun ... bench.py --gpus N --steps K --warmup W      # N replicas (utterance-sharded, no collective)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+A "step" is one forward of the hot path over one batch of 64 synthetic utterances (64 fbank x 160
+frames -> 512-d), BASELINE.json configs[1].  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "speaker-embeddings/sec (64-fbank x 160-frame -> 512-d)"
+FLOP_PER_EMB = 2306670592
+CONV_TC_FLOP_PER_EMB = 2296381440    # the 11 tensor-core convs: 8 x 3x3 (94,371,840 MAC) + 3 x 5x5 s2 (131,072,000 MAC)
+L2_BYTES = 126 * 1024 * 1024
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops_burst": d.get("bf16_tflops"), "tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def make_model(dtype, device):
+    """DeepSpeakerModel(512, 1211) with the reference's init and non-trivial BN statistics."""
+    import torch
+
+    from deepspeaker_pytorch_b200 import DeepSpeakerModel
+
+    torch.manual_seed(0)
+    m = DeepSpeakerModel(512, 1211, operand_dtype=dtype)
+    g = torch.Generator().manual_seed(1)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.weight.data.uniform_(0.5, 1.5, generator=g)
+            mod.bias.data.normal_(0, 0.1, generator=g)
+            mod.running_mean.normal_(0, 0.1, generator=g)
+            mod.running_var.uniform_(0.5, 1.5, generator=g)
+    return m.to(device).eval()
+
+
+def cpu_forward_timer(sd, B, T, budget_s, threads):
+    """Times the oracle's eval forward (restatement of /root/reference/model.py:185-218) on host cores."""
+    import torch
+
+    from oracle import rescnn_oracle as O
+
+    torch.set_num_threads(threads)
+    x = O.make_input(B, T, seed=0)
+    with torch.no_grad():
+        O.forward(sd, x)  # warm-up
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            O.forward(sd, x)
+            n += 1
+            el = time.perf_counter() - t0
+            if el > budget_s or n >= 50:
+                break
+    return B * n / el, n, el
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  /root/reference does not exist
+    on the GPU box, so this runs the oracle port (same PyTorch CPU kernels the reference dispatches to)."""
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import rescnn_oracle as O
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = {k: v for k, v in make_model("fp16", "cpu").state_dict().items()}
+    B, T = args.batch, args.frames
+    x = O.make_input(B, T, seed=0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.forward(sd, x)
+        t1 = time.perf_counter() - t0
+        # bound the whole run to ~2 minutes: shrink the per-step sample if needed
+        total = (args.steps + args.warmup) * t1
+        b = B if total <= 120 else max(1, int(B * 120 / total))
+        xs = x[:b]
+        for _ in range(args.warmup):
+            O.forward(sd, xs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(sd, xs)
+        el = time.perf_counter() - t0
+    val = b * args.steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "emb/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch-{B} embedding inference, synthetic 64x{T} fbank, eval mode (BASELINE configs[1])",
+                   "batch": B, "frames": T},
+        "cpu_baseline": {"value": val, "unit": "emb/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {b} utterances of the batch-{B} workload (oracle port of "
+                                   f"model.py:185-218 on torch CPU fp32 kernels)"},
+        "e2e": {"value": val, "unit": "emb/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=160)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from deepspeaker_pytorch_b200 import _lib as L
+
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, K, W = args.batch, args.frames, args.steps, args.warmup
+    model = make_model(args.dtype, dev)
+    in_bytes = B * T * 64 * 4
+    nbuf = L2_BYTES // in_bytes + 8  # rotating inputs larger than L2
+    g = torch.Generator(device=dev).manual_seed(rank)
+    xs = [torch.randn(B, 1, T, 64, device=dev, generator=g) for _ in range(nbuf)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- value: inputs resident in HBM ---------------------------------------------------------
+    with torch.no_grad():
+        for i in range(W):
+            model(xs[i % nbuf])
+        sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        e0.record()
+        for i in range(K):
+            model(xs[i % nbuf])
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        value = world * B * K / (ms * 1e-3)
+
+        # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region -----------
+        nhost = 8
+        xh = [torch.randn(B, 1, T, 64).pin_memory() for _ in range(nhost)]
+        oh = [torch.empty(B, 512).pin_memory() for _ in range(nhost)]
+        xd = [torch.empty(B, 1, T, 64, device=dev) for _ in range(2)]
+        for i in range(W):
+            xd[i % 2].copy_(xh[i % nhost], non_blocking=True)
+            oh[i % nhost].copy_(model(xd[i % 2]), non_blocking=True)
+        barrier()
+        e0.record()
+        for i in range(K):
+            xd[i % 2].copy_(xh[i % nhost], non_blocking=True)
+            oh[i % nhost].copy_(model(xd[i % 2]), non_blocking=True)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e_value = world * B * K / (ms_e2e * 1e-3)
+
+        # ---- roofline of the dominant kernel: per-launch CUDA-event times inside the forward ---------
+        eng = model._engine
+        import ctypes
+
+        L.check(eng.lib.dsk_set_profiling(eng.handle, 1))
+        buf = (ctypes.c_float * 32)()
+        n = ctypes.c_int32(0)
+        acc = None
+        nprof = 20
+        for i in range(nprof):
+            model(xs[i % nbuf])
+            L.check(eng.lib.dsk_get_launch_times(eng.handle, buf, 32, ctypes.byref(n)))
+            v = [buf[j] for j in range(n.value)]
+            acc = v if acc is None else [a + b for a, b in zip(acc, v)]
+        L.check(eng.lib.dsk_set_profiling(eng.handle, 0))
+        per_launch_ms = [a / nprof for a in acc]
+    conv_ms = sum(per_launch_ms[1:12])
+    step_ms_prof = sum(per_launch_ms)
+    peaks = load_peaks()
+    achieved = B * CONV_TC_FLOP_PER_EMB / (conv_ms * 1e-3) / 1e12
+    peak = peaks["tflops_sustained"] if (ms > 2000 and peaks["tflops_sustained"]) else peaks["tflops_burst"]
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "traffic": None,
+        "kernel": "conv_umma_kernel (11 launches per step: 8 x 3x3 s1 + 3 x 5x5 s2 implicit-GEMM convs)",
+        "flop_per_launch_set": B * CONV_TC_FLOP_PER_EMB, "launch_set_ms": conv_ms,
+        "share_of_step": conv_ms / step_ms_prof, "per_launch_ms": [round(x, 5) for x in per_launch_ms],
+        "peak_source": peaks["source"] + (" sustained" if peak == peaks["tflops_sustained"] else " burst"),
+    }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        v, n_it, el = cpu_forward_timer(sd, B, T, budget_s=12.0, threads=threads)
+        cpu_baseline = {"value": v, "unit": "emb/s", "cores": threads, "kind": "port",
+                        "sample": f"{n_it} forwards of the same batch-{B} workload in {el:.1f} s (oracle port of "
+                                  f"/root/reference/model.py:185-218, torch CPU fp32)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "emb/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"batch-{B} embedding inference, synthetic 64x{T} fbank, eval-mode BN, "
+                               f"DeepSpeakerModel(512,1211) random init (BASELINE configs[1])",
+                   "batch_per_gpu": B, "frames": T, "parallelism": f"replicas x{world} (utterance-sharded, no collective)",
+                   "operands": f"{args.dtype} tensor-core operands, fp32 accumulate/BN/fc/norm",
+                   "l2": f"inputs rotate over {nbuf} buffers = {nbuf * in_bytes >> 20} MiB > 126 MiB L2; "
+                         f"activations ({B * 1843200 >> 20} MiB/step) are rewritten every step"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "emb/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * 512 * 4,
+                "ms_per_step": ms_e2e / K, "api": "DeepSpeakerModel.forward on a device copy of pinned host input; "
+                                                  "embeddings copied back to pinned host memory"},
+        "gpu_launches": 15 * K,
+        "roofline": roofline,
+        "tflops_whole_step": B * FLOP_PER_EMB / (ms / K * 1e-3) / 1e12,
+    }
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,7 @@
+"""B200-native Deep Speaker hot path: drop-in for /root/reference/model.py's DeepSpeakerModel,
+TripletMarginLoss and PairwiseDistance, backed by hand-written sm_100a CUDA behind a C ABI
+(include/dsk.h, lib/libdsk.so)."""
+from .model import (DeepSpeakerModel, PairwiseDistance, TripletMarginLoss, allpairs_topk,  # noqa: F401
+                    select_hard_triplets)
+
+__all__ = ["DeepSpeakerModel", "PairwiseDistance", "TripletMarginLoss", "select_hard_triplets", "allpairs_topk"]

@@ -137,6 +137,10 @@ struct dsk_handle_s {
     std::vector<ConvLaunch> conv;  // index = conv index (0 unused)
   };
   std::map<std::pair<int, int>, Plan> plans;
+  // optional per-launch timing (dsk_set_profiling): events recorded around every kernel of a forward
+  bool profiling = false;
+  std::vector<cudaEvent_t> events;
+  int n_marks = 0;
 };
 
 namespace {
@@ -393,6 +397,7 @@ int32_t dsk_destroy(dsk_handle h) {
   cudaFree(h->conv1_w);
   cudaFree(h->fc_wq);
   cudaFree(h->ws);
+  for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   delete h;
   return DSK_OK;
 }
@@ -471,6 +476,17 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
   dsk_handle_s::Plan* pl;
   rc = get_plan(h, B, T, &pl);
   if (rc) return rc;
+  h->n_marks = 0;
+  auto mark = [&]() {
+    if (!h->profiling) return;
+    if (h->n_marks >= static_cast<int>(h->events.size())) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      h->events.push_back(e);
+    }
+    cudaEventRecord(h->events[h->n_marks++], s);
+  };
+  mark();
   // conv1 (+bn1 +clip)
   {
     const int hout = T / 2;
@@ -480,10 +496,12 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
     else
       dsk::conv1_kernel<false><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->scale[0], h->bias[0], (uint16_t*)pl->act[0], T, 1, 20.0f);
     KERNEL_CHECK();
+    mark();
   }
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
     rc = launch_conv(h, pl->conv[i], s);
     if (rc) return rc;
+    mark();
   }
   // tail
   {
@@ -493,6 +511,7 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
     else
       dsk::pool_time_kernel<false><<<B, 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC);
     KERNEL_CHECK();
+    mark();
     static bool fc_attr = false;
     const int fc_smem = 8 * 2048 * 4;
     if (!fc_attr) {
@@ -502,9 +521,30 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
     dim3 g((B + 7) / 8, h->emb / 64);
     dsk::fc_kernel<<<g, 256, fc_smem, s>>>(pl->pooled, h->fc_wq, h->fc_b, pl->fc_out, B, 2048, h->emb);
     KERNEL_CHECK();
+    mark();
     dsk::l2norm_kernel<<<B, 128, 0, s>>>(pl->fc_out, emb, nullptr, h->emb, 10.0f);
     KERNEL_CHECK();
+    mark();
   }
+  return DSK_OK;
+}
+
+int32_t dsk_set_profiling(dsk_handle h, int32_t enable) {
+  if (!h) return fail(DSK_ERR_INVALID, "null handle");
+  h->profiling = enable != 0;
+  h->n_marks = 0;
+  return DSK_OK;
+}
+
+int32_t dsk_get_launch_times(dsk_handle h, float* ms_out, int32_t cap, int32_t* n_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!ms_out || !n_out) return fail(DSK_ERR_INVALID, "dsk_get_launch_times: null output");
+  const int n = h->n_marks > 0 ? h->n_marks - 1 : 0;
+  if (n > cap) return fail(DSK_ERR_INVALID, "dsk_get_launch_times: need room for %d values", n);
+  if (n > 0) CUDA_TRY(cudaEventSynchronize(h->events[h->n_marks - 1]));
+  for (int i = 0; i < n; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_out[i], h->events[i], h->events[i + 1]));
+  *n_out = n;
   return DSK_OK;
 }
 

@@ -85,6 +85,13 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream);
 int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, int32_t mode,
                            void* stream);
 
+/* Per-launch device timing of the next dsk_rescnn_forward calls: when enabled, CUDA events are recorded on
+ * `stream` around every kernel of the forward (order: conv1, the 11 tensor-core convs in network order,
+ * pool, fc, l2norm).  dsk_get_launch_times waits for the last profiled forward (the only call in this
+ * library that blocks the host) and returns its per-launch milliseconds. Used by bench.py's roofline. */
+int32_t dsk_set_profiling(dsk_handle h, int32_t enable);
+int32_t dsk_get_launch_times(dsk_handle h, float* ms_out, int32_t cap, int32_t* n_out);
+
 /* One fused conv layer on NHWC 16-bit tensors: out = clip(conv(in, w)*scale + bias (+res)).
  * Building block of dsk_rescnn_forward, exported for unit tests against F.conv2d.
  * ksize/stride in {(3,1),(5,2)}; cin, cout multiples of 64; flags: 1 = add residual, 2 = clip to [0,clip_hi].

@@ -169,7 +169,6 @@ def allpairs_topk(E, labels, k: int):
     """BASELINE config 4 — NOT in the reference (parity unpinned).
     D[i,j] = PairwiseDistance(2)(e_i, e_j) (model.py:13-18); candidates have a different label;
     k smallest, ties -> lower index."""
-    E = E.double() if False else E
     N, D = E.shape
     eps = np.float32(1e-4 / D)
     En = E.numpy().astype(np.float32)

@@ -1,0 +1,61 @@
+"""Host-side mirror of the reference interface: names, state_dict keys, error behaviour (CPU only)."""
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import deepspeaker_pytorch_b200 as dsk
+
+
+def test_state_dict_keys_and_shapes_match_reference(golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))
+    m = dsk.DeepSpeakerModel(512, 16)
+    got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    assert got == ref
+
+
+def test_reference_checkpoint_roundtrip():
+    from oracle import rescnn_oracle as O
+
+    sd = O.make_state_dict(0, 16)
+    m = dsk.DeepSpeakerModel(512, 16)
+    m.load_state_dict(sd)                       # strict: every reference key is consumed
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    assert sum(p.numel() for p in dsk.DeepSpeakerModel(512, 1211).parameters()) == 12245371
+
+
+def test_init_follows_reference():
+    torch.manual_seed(0)
+    m = dsk.DeepSpeakerModel(512, 16)
+    w = m.model.layer3[0].conv1.weight
+    assert abs(w.std().item() - (2.0 / (9 * 256)) ** 0.5) < 2e-3      # model.py:114-117
+    assert torch.all(m.model.bn2.weight == 1) and torch.all(m.model.bn2.bias == 0)   # :118-120
+    assert m.model.fc.weight.shape == (512, 2048) and m.model.classifier.weight.shape == (16, 512)
+
+
+def test_no_cpu_fallback():
+    m = dsk.DeepSpeakerModel(512, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 1, 160, 64))
+    with pytest.raises(RuntimeError):
+        dsk.TripletMarginLoss(0.1).forward(torch.zeros(2, 4), torch.zeros(2, 4), torch.zeros(2, 4))
+    with pytest.raises(RuntimeError):
+        dsk.PairwiseDistance(2).forward(torch.zeros(2, 4), torch.zeros(2, 4))
+    with pytest.raises(ValueError):
+        dsk.DeepSpeakerModel(512, 16, feature_dim=40)
+    with pytest.raises(ValueError):
+        dsk.PairwiseDistance(1)
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "deepspeaker_pytorch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
+                assert not re.search(r"#include.*oracle|libdsk_oracle|c_oracle", src), f

@@ -1,0 +1,122 @@
+"""Pins the oracle (oracle/rescnn_oracle.py, oracle/dsk_oracle.c) against golden vectors produced by the
+reference's own model.py (tools/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import c_oracle as C
+from oracle import rescnn_oracle as O
+from tests.helpers import make_triplet_embeddings, rel_l2, sample_idx
+
+torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+
+
+def test_eval_forward_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "eval_forward.npz"))
+    sd = O.make_state_dict(0, 16)
+    for name in ("a", "b", "c"):
+        B, T, seed, scale = g[f"{name}_cfg"]
+        x = O.make_input(int(B), int(T), int(seed), float(scale))
+        taps = {}
+        with torch.no_grad():
+            e = O.forward(sd, x, taps=taps)
+        ref = torch.from_numpy(g[f"{name}_emb"])
+        assert rel_l2(e, ref) < 1e-5          # same ATen kernels, restated control flow
+        assert torch.allclose(e.norm(dim=1), torch.full((int(B),), 10.0), atol=1e-4)
+        for s in range(4):
+            k = 3 * s + 2
+            v = taps[k].flatten()[torch.from_numpy(g[f"{name}_tap{k}_idx"])]
+            assert np.allclose(v.numpy(), g[f"{name}_tap{k}_val"], rtol=1e-4, atol=1e-4)
+
+
+def test_input_layout_is_time_by_64():
+    """(B,1,T,64) works, (B,1,64,T) must not (fc expects 512*4)."""
+    sd = O.make_state_dict(0, 16)
+    with torch.no_grad():
+        assert O.forward(sd, torch.zeros(1, 1, 32, 64)).shape == (1, 512)
+        try:
+            O.forward(sd, torch.zeros(1, 1, 64, 32))
+            assert False, "transposed layout must fail"
+        except RuntimeError:
+            pass
+
+
+def test_loss_and_selection_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "triplet_loss.npz"))
+    a, p, n = make_triplet_embeddings()
+    # torch restatement
+    d_p, d_n = O.pairwise_distance(a, p), O.pairwise_distance(a, n)
+    assert np.allclose(d_p.numpy(), g["d_p"], rtol=1e-6) and np.allclose(d_n.numpy(), g["d_n"], rtol=1e-6)
+    assert abs(O.triplet_margin_loss(a, p, n, 0.1).item() - float(g["loss"])) < 1e-6
+    assert np.array_equal(O.margin_select(d_p, d_n, 0.1), g["hard_idx"])
+    # C restatement (canonical summation order shared with the CUDA kernels)
+    loss, cdp, cdn = C.triplet_loss(a.numpy(), p.numpy(), n.numpy(), 0.1)
+    assert np.allclose(cdp, g["d_p"], rtol=1e-6) and np.allclose(cdn, g["d_n"], rtol=1e-6)
+    assert abs(loss - float(g["loss"])) < 1e-6
+    assert np.array_equal(C.margin_select(cdp, cdn, 0.1), g["hard_idx"])
+    assert np.allclose(C.pairwise_distance(a.numpy(), p.numpy()), g["d_p"], rtol=1e-6)
+    # selected-subset loss, train_triplet.py:275
+    h = g["hard_idx"]
+    assert abs(O.triplet_margin_loss(a[h], p[h], n[h], 0.1).item() - float(g["selected_loss"])) < 1e-6
+
+
+def test_selection_edge_cases():
+    # empty selection (train_triplet.py:263-264 skips the batch), full selection, ties at the margin
+    d_p = np.array([1.0, 1.0, 1.0, 1.0], np.float32)
+    assert len(C.margin_select(d_p, d_p + 5.0, 0.1)) == 0
+    assert np.array_equal(C.margin_select(d_p, d_p, 0.1), np.arange(4))
+    d_n = d_p + np.float32(0.1)
+    exp = np.where((d_n - d_p) < np.float32(0.1))[0]     # strict '<' in fp32 arithmetic
+    assert np.array_equal(C.margin_select(d_p, d_n, 0.1), exp)
+
+
+def test_train_step_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "train_step.npz"))
+    B, T, s0, s1, s2, scale = g["cfg"]
+    sd = O.make_state_dict(0, 16)
+    xa, xp, xn = (O.make_input(int(B), int(T), int(s), float(scale)) for s in (s0, s1, s2))
+    stats = {}
+    loss, grads, oa, op, on = O.triplet_step_branch_a(sd, xa, xp, xn, 0.1, stats)
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    assert rel_l2(oa, torch.from_numpy(g["out_a"])) < 1e-5
+    n_checked = 0
+    for k, gr in grads.items():
+        if "gnorm/" + k not in g:
+            assert gr is None or "classifier" in k     # classifier gets no gradient in branch A
+            continue
+        ref_norm = float(g["gnorm/" + k])
+        assert abs(gr.double().norm().item() - ref_norm) <= 2e-3 * ref_norm + 1e-7, k
+        ix = torch.from_numpy(g["gidx/" + k])
+        assert np.allclose(gr.flatten()[ix].numpy(), g["gval/" + k], rtol=5e-3, atol=2e-3 * ref_norm / np.sqrt(gr.numel())), k
+        n_checked += 1
+    assert n_checked == 38
+    for k, v in stats.items():     # running stats after three train-mode forwards
+        assert np.allclose(v.numpy(), g["stat/" + k], rtol=1e-4, atol=1e-5), k
+
+
+def test_allpairs_matches_reference_distance(golden_dir):
+    g = np.load(os.path.join(golden_dir, "allpairs.npz"))
+    N, D, seed = (int(v) for v in g["seed"])
+    gen = torch.Generator().manual_seed(seed)
+    E = torch.randn(N, D, generator=gen)
+    E = 10.0 * E / E.norm(dim=1, keepdim=True)
+    labels = torch.from_numpy(g["labels"])
+    k = 5
+    idx, val = C.allpairs_topk(E.numpy(), labels.numpy(), k)
+    Dm = g["dist"].copy()
+    for i in range(N):
+        # values are the reference PairwiseDistance of the chosen pairs
+        assert np.allclose(val[i], Dm[i, idx[i]], rtol=1e-5)
+        cand = Dm[i].copy()
+        cand[labels.numpy() == labels.numpy()[i]] = np.inf
+        # random 10-normalised embeddings are nearly equidistant, so the k-th place can be a last-ulp
+        # tie under a different fp32 summation order: the chosen set must be optimal up to 1e-5 relative
+        kth = np.sort(cand)[k - 1]
+        assert np.all(labels.numpy()[idx[i]] != labels.numpy()[i])
+        assert len(set(idx[i].tolist())) == k
+        assert Dm[i, idx[i]].max() <= kth * (1 + 1e-5)
+        assert np.all(np.diff(val[i]) >= 0)
+    i2, v2 = O.allpairs_topk(E, labels, k)
+    assert np.allclose(v2, val, rtol=1e-5)
+    assert (i2 == idx).mean() > 0.98

@@ -132,8 +132,17 @@ def golden_allpairs():
     print("allpairs.npz", Dm.shape)
 
 
+def golden_keys():
+    import json
+    m = R.DeepSpeakerModel(512, NUM_CLASSES)
+    keys = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    json.dump(keys, open(os.path.join(OUT, "state_dict_keys.json"), "w"), indent=0)
+    print("state_dict_keys.json", len(keys))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    golden_keys()
     torch.set_num_threads(8)
     golden_eval()
     golden_loss()
