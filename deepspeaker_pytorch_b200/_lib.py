@@ -89,6 +89,10 @@ SIGNATURES = {
     "dsk_destroy": (c_int32, [c_void_p]),
     "dsk_load_weights": (c_int32, [c_void_p, POINTER(DskWeights), c_void_p]),
     "dsk_rescnn_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "dsk_rescnn_forward_train": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_void_p), c_void_p]),
+    "dsk_rescnn_backward": (c_int32, [c_void_p, c_void_p, c_void_p, POINTER(DskGrads), c_void_p]),
+    "dsk_train_ctx_release": (c_int32, [c_void_p, c_void_p]),
+    "dsk_set_loss_scale": (c_int32, [c_void_p, c_float]),
     "dsk_set_profiling": (c_int32, [c_void_p, c_int32]),
     "dsk_get_launch_times": (c_int32, [c_void_p, c_void_p, c_int32, POINTER(c_int32)]),
     "dsk_conv2d_nhwc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,

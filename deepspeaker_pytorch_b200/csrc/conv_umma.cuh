@@ -39,8 +39,12 @@ struct ConvParams {
   float clip_hi;
   const float* scale;  // [cout] or nullptr (=1)
   const float* bias;   // [cout] or nullptr (=0)
-  // per-tap source offsets in the 5-D input view (c, w2, ph, h2, n)
+  // output placement in the 5-D output view (c, w, ph, h, n): channel base and parity row.  Plain NHWC
+  // outputs use (0, 0); the stride-2 data-gradient writes parity class (ph, pw) with out_c_base = pw*C.
+  int out_c_base, out_ph;
+  // per-tap source offsets in the 5-D input view (c, w2, ph, h2, n) and weight slice index
   int16_t tap_c[kMaxTaps];
+  int8_t tap_w[kMaxTaps];
   int8_t tap_dw[kMaxTaps];
   int8_t tap_ph[kMaxTaps];
   int8_t tap_dh[kMaxTaps];
@@ -150,7 +154,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
           tma_load_5d(smem_a + stage * kATileBytes, &tmA, &full_bar[stage], p.tap_c[tap] + ch * kKStep,
                       w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
-          tma_load_3d(smem_b + stage * S::kBTileBytes, &tmB, &full_bar[stage], ch * kKStep, c0, tap);
+          tma_load_3d(smem_b + stage * S::kBTileBytes, &tmB, &full_bar[stage], ch * kKStep, c0, p.tap_w[tap]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -218,7 +222,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (has_res) {
           if (etid == 0) {
             mbar_arrive_expect_tx(&res_bar[buf], kATileBytes);
-            tma_load_4d(stg, &tmRes, &res_bar[buf], c0 + j * 64, w0, h0, n0);
+            tma_load_5d(stg, &tmRes, &res_bar[buf], p.out_c_base + c0 + j * 64, w0, p.out_ph, h0, n0);
           }
         }
         uint32_t v0[32], v1[32];
@@ -265,7 +269,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (etid == 0) {
-          tma_store_4d(&tmOut, stg, c0 + j * 64, w0, h0, n0);
+          tma_store_5d(&tmOut, stg, p.out_c_base + c0 + j * 64, w0, p.out_ph, h0, n0);
           tma_store_commit();
         }
         buf ^= 1;

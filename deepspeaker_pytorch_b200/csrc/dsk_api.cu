@@ -16,6 +16,7 @@
 #include "loss_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "train_kernels.cuh"
+#include "wgrad_umma.cuh"
 
 namespace {
 
@@ -96,6 +97,13 @@ struct ConvLaunch {
   int grid = 0;
 };
 
+struct WgradLaunch {
+  CUtensorMap tmG, tmX;
+  dsk::WgradParams p;
+  int n_tile = 0;
+  int grid = 0;
+};
+
 struct LayerCfg {
   int cin, cout, ksize, stride;
 };
@@ -118,7 +126,7 @@ struct dsk_handle_s {
   int emb = 512;
   // packed parameters
   void* wpk[DSK_NUM_CONV] = {};       // 16-bit [tap][cout][cin]   (conv1: nullptr)
-  void* wpk_dgrad[DSK_NUM_CONV] = {}; // 16-bit rotated/transposed for stride-1 dgrad
+  void* wpk_dgrad[DSK_NUM_CONV] = {}; // 16-bit [tap][cin][cout] for the data gradient (rotated for stride 1)
   float* conv1_w = nullptr;           // fp32 [64][25]
   float* scale[DSK_NUM_CONV] = {};    // folded eval BN
   float* bias[DSK_NUM_CONV] = {};
@@ -137,18 +145,50 @@ struct dsk_handle_s {
     std::vector<ConvLaunch> conv;  // index = conv index (0 unused)
   };
   std::map<std::pair<int, int>, Plan> plans;
+  // training
+  float* ones = nullptr;   // [512] = 1
+  float* zeros = nullptr;  // [512] = 0
+  float loss_scale = 0.f;  // 0 = automatic
+  std::vector<dsk_train_ctx_s*> ctx_pool;
   // optional per-launch timing (dsk_set_profiling): events recorded around every kernel of a forward
   bool profiling = false;
   std::vector<cudaEvent_t> events;
   int n_marks = 0;
 };
 
+// Everything one train-mode forward saves for its backward (one per a/p/n call, train_triplet.py:215).
+struct dsk_train_ctx_s {
+  int B = 0, T = 0;
+  bool in_use = false;
+  bool forward_done = false;
+  const float* x = nullptr;            // borrowed: the caller keeps the input alive until backward
+  uint8_t* base = nullptr;             // one allocation
+  void* raw[DSK_NUM_CONV] = {};        // conv outputs before BN (16-bit NHWC)
+  void* y[DSK_NUM_CONV] = {};          // after BN (+res) + clip (16-bit NHWC)
+  void* yT[DSK_NUM_CONV] = {};         // channel-major copy of y[i], i < 11 (operand of conv i+1's weight gradient)
+  dsk::TransposeGeom tgY[DSK_NUM_CONV];
+  dsk::TransposeGeom tgG[DSK_NUM_CONV];
+  float* mean[DSK_NUM_CONV] = {};
+  float* rstd[DSK_NUM_CONV] = {};
+  float *pooled = nullptr, *fc_out = nullptr, *inv_norm = nullptr;
+  float *scale_t = nullptr, *shift_t = nullptr, *partial = nullptr, *coef = nullptr;
+  float *g_fc = nullptr, *dP = nullptr, *dwacc = nullptr, *c1part = nullptr;
+  void *gA = nullptr, *gB = nullptr, *G = nullptr, *GT = nullptr, *gres = nullptr;
+  size_t gt_bytes = 0;
+  ConvLaunch conv[DSK_NUM_CONV];       // forward convs 1..11 (raw output, no epilogue math)
+  ConvLaunch dgrad[DSK_NUM_CONV][4];
+  int n_dgrad[DSK_NUM_CONV] = {};
+  WgradLaunch wgrad[DSK_NUM_CONV];
+};
+
 namespace {
 
-// Choose the pixel box (wt, hb, nb) with wt*hb*nb == 128 that wastes the fewest rows.
-void choose_tile(int B, int Hout, int Wout, int& wt, int& hb, int& nb) {
-  wt = Wout < 128 ? Wout : 128;
-  const int rows = 128 / wt;  // h*n rows per tile
+constexpr int kStatBlocksMax = 1200;
+
+// Choose the pixel box (wt, hb, nb) with wt*hb*nb == total that wastes the fewest rows.
+void choose_tile(int B, int Hout, int Wout, int total, int& wt, int& hb, int& nb) {
+  wt = Wout < total ? Wout : total;
+  const int rows = total / wt;  // h*n rows per tile
   long best = -1;
   hb = 1;
   nb = rows;
@@ -193,93 +233,232 @@ int launch_conv(const dsk_handle_s* h, const ConvLaunch& L, cudaStream_t s) {
   return fail(DSK_ERR_INVALID, "unsupported N tile %d", L.n_tile);
 }
 
-// Build descriptors + parameters for one fused conv layer on NHWC 16-bit tensors.
+// A 5-D TMA view (dims innermost first; str[i] = byte stride of dim i+1) of a 16-bit tensor.
+struct View5 {
+  const void* ptr;
+  uint64_t dims[5];
+  uint64_t str[4];
+};
+
+// NHWC tensor as (c, w, 1, h, n)
+View5 nhwc_view(const void* ptr, int B, int H, int W, int C) {
+  View5 v;
+  v.ptr = ptr;
+  v.dims[0] = C; v.dims[1] = W; v.dims[2] = 1; v.dims[3] = H; v.dims[4] = B;
+  v.str[0] = 2ull * C; v.str[1] = 2ull * W * C; v.str[2] = 2ull * W * C; v.str[3] = 2ull * H * W * C;
+  return v;
+}
+// NHWC tensor with even H, W as parity view (pw*C + c, w/2, h&1, h/2, n): what a stride-2 conv reads / its
+// data-gradient writes.
+View5 nhwc_parity_view(const void* ptr, int B, int H, int W, int C) {
+  View5 v;
+  v.ptr = ptr;
+  v.dims[0] = 2ull * C; v.dims[1] = W / 2; v.dims[2] = 2; v.dims[3] = H / 2; v.dims[4] = B;
+  v.str[0] = 4ull * C; v.str[1] = 2ull * W * C; v.str[2] = 4ull * W * C; v.str[3] = 2ull * H * W * C;
+  return v;
+}
+
+struct TapTable {
+  int n = 0;
+  int16_t c[dsk::kMaxTaps];
+  int8_t w[dsk::kMaxTaps], dw[dsk::kMaxTaps], ph[dsk::kMaxTaps], dh[dsk::kMaxTaps];
+  void add(int c_, int w_, int dw_, int ph_, int dh_) {
+    c[n] = (int16_t)c_; w[n] = (int8_t)w_; dw[n] = (int8_t)dw_; ph[n] = (int8_t)ph_; dh[n] = (int8_t)dh_;
+    ++n;
+  }
+};
+
+// Generic builder: out[pixel grid Hgrid x Wgrid x B][n_out] = epilogue( sum_taps A(tap-shifted)[.., k] * Wt[tap][n_out][k] ).
+int build_conv_core(const dsk_handle_s* h, ConvLaunch* L, const View5& a, const void* wpk, int k_ch, int n_out,
+                    int w_slices, const View5& o, const void* res, int B, int Hgrid, int Wgrid, const TapTable& taps,
+                    int flags, float clip_hi, const float* scale, const float* bias, int out_c_base, int out_ph) {
+  if (k_ch % 64 || n_out % 64 || k_ch < 64 || n_out < 64 || n_out > 512)
+    return fail(DSK_ERR_INVALID, "conv: channel counts must be multiples of 64 and <= 512 outputs (got %d, %d)", k_ch, n_out);
+  if (Wgrid > 128 || 128 % Wgrid) return fail(DSK_ERR_INVALID, "conv: output width %d must divide 128", Wgrid);
+  const bool bf = h->bf16;
+  dsk::ConvParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  choose_tile(B, Hgrid, Wgrid, 128, p.wt, p.hb, p.nb);
+  p.tiles_w = (Wgrid + p.wt - 1) / p.wt;
+  p.tiles_h = (Hgrid + p.hb - 1) / p.hb;
+  p.tiles_n = (B + p.nb - 1) / p.nb;
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  // N tile: the largest of {256,128,64} dividing n_out that still gives every SM a tile; else the smallest.
+  int n_tile = 64;
+  for (int cand : {256, 128, 64}) {
+    if (n_out % cand) continue;
+    n_tile = cand;
+    if (static_cast<long>(tiles_m) * (n_out / cand) >= h->num_sms) break;
+  }
+  L->n_tile = n_tile;
+  p.tiles_c = n_out / n_tile;
+  p.taps = taps.n;
+  p.cin_chunks = k_ch / 64;
+  p.cout = n_out;
+  p.flags = flags;
+  p.clip_hi = clip_hi;
+  p.scale = scale;
+  p.bias = bias;
+  p.out_c_base = out_c_base;
+  p.out_ph = out_ph;
+  for (int t = 0; t < taps.n; ++t) {
+    p.tap_c[t] = taps.c[t];
+    p.tap_w[t] = taps.w[t];
+    p.tap_dw[t] = taps.dw[t];
+    p.tap_ph[t] = taps.ph[t];
+    p.tap_dh[t] = taps.dh[t];
+  }
+  const int num_tiles = tiles_m * p.tiles_c;
+  L->grid = num_tiles < h->num_sms ? num_tiles : h->num_sms;
+  uint32_t boxA[5] = {64, (uint32_t)p.wt, 1, (uint32_t)p.hb, (uint32_t)p.nb};
+  int rc = make_tmap(&L->tmA, bf, a.ptr, 5, a.dims, a.str, boxA);
+  if (rc) return rc;
+  uint64_t wd[3] = {(uint64_t)k_ch, (uint64_t)n_out, (uint64_t)w_slices};
+  uint64_t ws[2] = {2ull * k_ch, 2ull * k_ch * n_out};
+  uint32_t wb[3] = {64, (uint32_t)n_tile, 1};
+  rc = make_tmap(&L->tmB, bf, wpk, 3, wd, ws, wb);
+  if (rc) return rc;
+  rc = make_tmap(&L->tmOut, bf, o.ptr, 5, o.dims, o.str, boxA);
+  if (rc) return rc;
+  return make_tmap(&L->tmRes, bf, (flags & dsk::CONV_RESIDUAL) ? res : o.ptr, 5, o.dims, o.str, boxA);
+}
+
+// Forward conv layer on NHWC 16-bit tensors (3x3 s1 p1 or 5x5 s2 p2).
 int build_conv(const dsk_handle_s* h, ConvLaunch* L, const void* in, const void* wpk, const float* scale,
                const float* bias, const void* res, void* out, int B, int Hin, int Win, int cin, int cout, int ksize,
                int stride, int flags, float clip_hi) {
   if (!((ksize == 3 && stride == 1) || (ksize == 5 && stride == 2)))
     return fail(DSK_ERR_INVALID, "conv: only 3x3 s1 p1 and 5x5 s2 p2 are supported (got k=%d s=%d)", ksize, stride);
-  if (cin % 64 || cout % 64 || cin < 64 || cout < 64 || cout > 512)
-    return fail(DSK_ERR_INVALID, "conv: cin/cout must be multiples of 64 and cout <= 512 (got %d, %d)", cin, cout);
   if (stride == 2 && ((Hin & 1) || (Win & 1)))
     return fail(DSK_ERR_INVALID, "conv: stride-2 input must have even H and W (got %d x %d)", Hin, Win);
+  if (cin % 64 || cin < 64) return fail(DSK_ERR_INVALID, "conv: cin must be a multiple of 64 (got %d)", cin);
   const int Hout = Hin / stride, Wout = Win / stride;
-  if (Wout > 128 && Wout % 128) return fail(DSK_ERR_INVALID, "conv: unsupported output width %d", Wout);
-  if (128 % (Wout < 128 ? Wout : 128)) return fail(DSK_ERR_INVALID, "conv: output width %d must divide 128", Wout);
+  TapTable tt;
+  for (int r = 0; r < ksize; ++r)
+    for (int s = 0; s < ksize; ++s) {
+      if (stride == 1)
+        tt.add(0, r * ksize + s, s - 1, 0, r - 1);
+      else  // input col = 2*w - 2 + s -> (w2 = w + floor((s-2)/2), parity = s & 1); same for rows
+        tt.add((s & 1) * cin, r * ksize + s, (s - 2) >> 1, r & 1, (r - 2) >> 1);
+    }
+  const View5 a = stride == 1 ? nhwc_view(in, B, Hin, Win, cin) : nhwc_parity_view(in, B, Hin, Win, cin);
+  const View5 o = nhwc_view(out, B, Hout, Wout, cout);
+  return build_conv_core(h, L, a, wpk, cin, cout, ksize * ksize, o, res, B, Hout, Wout, tt, flags, clip_hi, scale, bias,
+                         0, 0);
+}
+
+// Data gradient of a 3x3 s1 p1 conv: g_in = conv(G, rot180(W)^T) (+ res).  G (B,H,W,cout) -> g_in (B,H,W,cin).
+int build_dgrad_s1(const dsk_handle_s* h, ConvLaunch* L, const void* G, const void* wpk_dgrad, const void* res,
+                   void* gin, int B, int H, int W, int cin, int cout) {
+  TapTable tt;
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) tt.add(0, r * 3 + s, s - 1, 0, r - 1);
+  return build_conv_core(h, L, nhwc_view(G, B, H, W, cout), wpk_dgrad, cout, cin, 9, nhwc_view(gin, B, H, W, cin), res,
+                         B, H, W, tt, res ? dsk::CONV_RESIDUAL : 0, 0.f, nullptr, nullptr, 0, 0);
+}
+
+// Data gradient of a 5x5 s2 p2 conv, parity class (ph, pw) of the input pixels:
+//   g_in[2*h2+ph][2*w2+pw] = sum_{r = ph (mod 2), s = pw (mod 2)} G[h2 + (ph+2-r)/2][w2 + (pw+2-s)/2] . W[:, :, r, s]
+// G (B,Hout,Wout,cout) -> g_in (B,2*Hout,2*Wout,cin) written through its parity view.
+int build_dgrad_s2(const dsk_handle_s* h, ConvLaunch* L, const void* G, const void* wpk_dgrad, void* gin, int B,
+                   int Hout, int Wout, int cin, int cout, int ph, int pw) {
+  TapTable tt;
+  for (int r = ph; r < 5; r += 2)
+    for (int s = pw; s < 5; s += 2) tt.add(0, r * 5 + s, (pw + 2 - s) / 2, 0, (ph + 2 - r) / 2);
+  return build_conv_core(h, L, nhwc_view(G, B, Hout, Wout, cout), wpk_dgrad, cout, cin, 25,
+                         nhwc_parity_view(gin, B, 2 * Hout, 2 * Wout, cin), nullptr, B, Hout, Wout, tt, 0, 0.f, nullptr,
+                         nullptr, pw * cin, ph);
+}
+
+// ---- weight gradient --------------------------------------------------------------------------------------------
+// channel-major 16-bit tensor [c][n][plane][Hp][Wp] as the TMA view (w, h, plane, n, c)
+View5 cmajor_view(const void* ptr, int N, int planes, int Hp, int Wp, int C) {
+  View5 v;
+  v.ptr = ptr;
+  v.dims[0] = Wp; v.dims[1] = Hp; v.dims[2] = planes; v.dims[3] = N; v.dims[4] = C;
+  v.str[0] = 2ull * Wp; v.str[1] = 2ull * Hp * Wp; v.str[2] = 2ull * planes * Hp * Wp;
+  v.str[3] = 2ull * N * planes * Hp * Wp;
+  return v;
+}
+
+// dW[tap][cout][cin] += GT (x) XT over the pixel grid (Hg x Wg(p) x N).  ksize/stride as the forward conv.
+int build_wgrad(const dsk_handle_s* h, WgradLaunch* L, const void* GT, const void* XT, int N, int Hg, int Wgp,
+                int x_planes, int cout, int cin, int ksize, int stride, float* dwacc) {
   const bool bf = h->bf16;
-  dsk::ConvParams& p = L->p;
+  dsk::WgradParams& p = L->p;
   memset(&p, 0, sizeof(p));
-  choose_tile(B, Hout, Wout, p.wt, p.hb, p.nb);
-  p.tiles_w = (Wout + p.wt - 1) / p.wt;
-  p.tiles_h = (Hout + p.hb - 1) / p.hb;
-  p.tiles_n = (B + p.nb - 1) / p.nb;
-  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-  // N tile: the largest of {256,128,64} dividing cout that still gives every SM a tile; else the smallest.
-  int n_tile = 64;
-  for (int cand : {256, 128, 64}) {
-    if (cout % cand) continue;
-    n_tile = cand;
-    if (static_cast<long>(tiles_m) * (cout / cand) >= h->num_sms) break;
-  }
-  L->n_tile = n_tile;
-  p.tiles_c = cout / n_tile;
+  if (Wgp < 8 || Wgp > 64 || 64 % Wgp) return fail(DSK_ERR_INVALID, "wgrad: row pitch %d unsupported", Wgp);
+  choose_tile(N, Hg, Wgp, 64, p.kw, p.kh, p.kn);
+  p.chunks_w = (Wgp + p.kw - 1) / p.kw;
+  p.chunks_h = (Hg + p.kh - 1) / p.kh;
+  p.chunks_n = (N + p.kn - 1) / p.kn;
   p.taps = ksize * ksize;
-  p.cin_chunks = cin / 64;
   p.cout = cout;
-  p.flags = flags;
-  p.clip_hi = clip_hi;
-  p.scale = scale;
-  p.bias = bias;
+  p.cin = cin;
+  p.co_tiles = (cout + 127) / 128;
+  const int n_tile = cin >= 256 ? 256 : (cin >= 128 ? 128 : 64);
+  L->n_tile = n_tile;
+  p.ci_tiles = (cin + n_tile - 1) / n_tile;
+  p.dw = dwacc;
   for (int r = 0; r < ksize; ++r)
     for (int s = 0; s < ksize; ++s) {
       const int t = r * ksize + s;
       if (stride == 1) {
-        p.tap_c[t] = 0;
-        p.tap_dw[t] = static_cast<int8_t>(s - 1);
-        p.tap_ph[t] = 0;
-        p.tap_dh[t] = static_cast<int8_t>(r - 1);
+        p.tap_dw[t] = (int8_t)(s - 1);
+        p.tap_dh[t] = (int8_t)(r - 1);
+        p.tap_plane[t] = 0;
       } else {
-        // input col = 2*w - 2 + s  ->  (w2 = w + floor((s-2)/2), parity = s & 1); same for rows
-        p.tap_c[t] = static_cast<int16_t>((s & 1) * cin);
-        p.tap_dw[t] = static_cast<int8_t>((s - 2) >> 1);  // arithmetic shift = floor
-        p.tap_ph[t] = static_cast<int8_t>(r & 1);
-        p.tap_dh[t] = static_cast<int8_t>((r - 2) >> 1);
+        p.tap_dw[t] = (int8_t)((s - 2) >> 1);
+        p.tap_dh[t] = (int8_t)((r - 2) >> 1);
+        p.tap_plane[t] = (int8_t)((r & 1) * 2 + (s & 1));
       }
     }
-  const int num_tiles = tiles_m * p.tiles_c;
-  L->grid = num_tiles < h->num_sms ? num_tiles : h->num_sms;
+  const int total_chunks = p.chunks_w * p.chunks_h * p.chunks_n;
+  const int items0 = p.taps * p.co_tiles * p.ci_tiles;
+  int ksplit = (2 * h->num_sms + items0 - 1) / items0;
+  const int max_split = total_chunks / 8 > 0 ? total_chunks / 8 : 1;
+  if (ksplit > max_split) ksplit = max_split;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = ksplit;
+  const int items = items0 * ksplit;
+  L->grid = items < h->num_sms ? items : h->num_sms;
+  const View5 g = cmajor_view(GT, N, 1, Hg, Wgp, cout);
+  const View5 x = cmajor_view(XT, N, x_planes, Hg, Wgp, cin);
+  uint32_t boxG[5] = {(uint32_t)p.kw, (uint32_t)p.kh, 1, (uint32_t)p.kn, 128};
+  uint32_t boxX[5] = {(uint32_t)p.kw, (uint32_t)p.kh, 1, (uint32_t)p.kn, (uint32_t)n_tile};
+  int rc = make_tmap(&L->tmG, bf, g.ptr, 5, g.dims, g.str, boxG);
+  if (rc) return rc;
+  return make_tmap(&L->tmX, bf, x.ptr, 5, x.dims, x.str, boxX);
+}
 
-  // A: 5-D view (c, w2, ph, h2, n) of the NHWC input
-  {
-    uint64_t dims[5], str[4];
-    if (stride == 1) {
-      dims[0] = cin; dims[1] = Win; dims[2] = 1; dims[3] = Hin; dims[4] = B;
-      str[0] = 2ull * cin; str[1] = 2ull * Win * cin; str[2] = 2ull * Win * cin; str[3] = 2ull * Hin * Win * cin;
-    } else {
-      dims[0] = 2ull * cin; dims[1] = Win / 2; dims[2] = 2; dims[3] = Hin / 2; dims[4] = B;
-      str[0] = 4ull * cin; str[1] = 2ull * Win * cin; str[2] = 4ull * Win * cin; str[3] = 2ull * Hin * Win * cin;
-    }
-    uint32_t box[5] = {64, (uint32_t)p.wt, 1, (uint32_t)p.hb, (uint32_t)p.nb};
-    int rc = make_tmap(&L->tmA, bf, in, 5, dims, str, box);
-    if (rc) return rc;
+template <int N_TILE, bool BF16>
+int launch_wgrad_t(const WgradLaunch& L, cudaStream_t s) {
+  auto kern = dsk::wgrad_umma_kernel<N_TILE, BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dsk::WgradSmem<N_TILE>::kTotal));
+    attr_set = true;
   }
-  {  // B: (cin, cout, taps)
-    uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)p.taps};
-    uint64_t str[2] = {2ull * cin, 2ull * cin * cout};
-    uint32_t box[3] = {64, (uint32_t)n_tile, 1};
-    int rc = make_tmap(&L->tmB, bf, wpk, 3, dims, str, box);
-    if (rc) return rc;
-  }
-  {  // out / residual: (cout, Wout, Hout, B)
-    uint64_t dims[4] = {(uint64_t)cout, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)B};
-    uint64_t str[3] = {2ull * cout, 2ull * Wout * cout, 2ull * Hout * Wout * cout};
-    uint32_t box[4] = {64, (uint32_t)p.wt, (uint32_t)p.hb, (uint32_t)p.nb};
-    int rc = make_tmap(&L->tmOut, bf, out, 4, dims, str, box);
-    if (rc) return rc;
-    rc = make_tmap(&L->tmRes, bf, (flags & dsk::CONV_RESIDUAL) ? res : out, 4, dims, str, box);
-    if (rc) return rc;
-  }
+  kern<<<L.grid, 256, dsk::WgradSmem<N_TILE>::kTotal, s>>>(L.tmG, L.tmX, L.p);
+  KERNEL_CHECK();
   return DSK_OK;
+}
+
+int launch_wgrad(const dsk_handle_s* h, const WgradLaunch& L, cudaStream_t s) {
+  if (h->bf16) {
+    switch (L.n_tile) {
+      case 64: return launch_wgrad_t<64, true>(L, s);
+      case 128: return launch_wgrad_t<128, true>(L, s);
+      case 256: return launch_wgrad_t<256, true>(L, s);
+    }
+  } else {
+    switch (L.n_tile) {
+      case 64: return launch_wgrad_t<64, false>(L, s);
+      case 128: return launch_wgrad_t<128, false>(L, s);
+      case 256: return launch_wgrad_t<256, false>(L, s);
+    }
+  }
+  return fail(DSK_ERR_INVALID, "unsupported wgrad N tile %d", L.n_tile);
 }
 
 int check_handle(dsk_handle h) {
@@ -381,6 +560,16 @@ int32_t dsk_create(dsk_handle* out, int32_t device, int32_t operand) {
   h->device = device;
   h->bf16 = operand == DSK_BF16;
   h->num_sms = prop.multiProcessorCount;
+  {
+    std::vector<float> one(512, 1.0f);
+    if (cudaMalloc(reinterpret_cast<void**>(&h->ones), 512 * 4) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&h->zeros), 512 * 4) != cudaSuccess ||
+        cudaMemcpy(h->ones, one.data(), 512 * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(h->zeros, 0, 512 * 4) != cudaSuccess) {
+      delete h;
+      return fail(DSK_ERR_CUDA, "dsk_create: device allocation failed");
+    }
+  }
   *out = h;
   return DSK_OK;
 }
@@ -397,6 +586,12 @@ int32_t dsk_destroy(dsk_handle h) {
   cudaFree(h->conv1_w);
   cudaFree(h->fc_wq);
   cudaFree(h->ws);
+  cudaFree(h->ones);
+  cudaFree(h->zeros);
+  for (dsk_train_ctx_s* c : h->ctx_pool) {
+    cudaFree(c->base);
+    delete c;
+  }
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   delete h;
   return DSK_OK;
@@ -437,17 +632,15 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
     }
     if (!h->wpk[i]) {
       CUDA_TRY(cudaMalloc(&h->wpk[i], n * 2));
-      if (c.stride == 1) CUDA_TRY(cudaMalloc(&h->wpk_dgrad[i], n * 2));
+      CUDA_TRY(cudaMalloc(&h->wpk_dgrad[i], n * 2));
     }
     const int blocks = static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
     if (h->bf16) {
       dsk::pack_conv_weight_kernel<true><<<blocks, 256, 0, s>>>(w->conv_w[i], (uint16_t*)h->wpk[i], c.cout, c.cin, taps);
-      if (c.stride == 1)
-        dsk::pack_conv_weight_dgrad_kernel<true><<<blocks, 256, 0, s>>>(w->conv_w[i], (uint16_t*)h->wpk_dgrad[i], c.cout, c.cin, taps);
+      dsk::pack_conv_weight_dgrad_kernel<true><<<blocks, 256, 0, s>>>(w->conv_w[i], (uint16_t*)h->wpk_dgrad[i], c.cout, c.cin, taps, c.stride == 1);
     } else {
       dsk::pack_conv_weight_kernel<false><<<blocks, 256, 0, s>>>(w->conv_w[i], (uint16_t*)h->wpk[i], c.cout, c.cin, taps);
-      if (c.stride == 1)
-        dsk::pack_conv_weight_dgrad_kernel<false><<<blocks, 256, 0, s>>>(w->conv_w[i], (uint16_t*)h->wpk_dgrad[i], c.cout, c.cin, taps);
+      dsk::pack_conv_weight_dgrad_kernel<false><<<blocks, 256, 0, s>>>(w->conv_w[i], (uint16_t*)h->wpk_dgrad[i], c.cout, c.cin, taps, c.stride == 1);
     }
     KERNEL_CHECK();
   }
@@ -490,7 +683,7 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
   // conv1 (+bn1 +clip)
   {
     const int hout = T / 2;
-    const int blocks = B * ((hout + 3) / 4);
+    const int blocks = B * ((hout + 7) / 8);
     if (h->bf16)
       dsk::conv1_kernel<true><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->scale[0], h->bias[0], (uint16_t*)pl->act[0], T, 1, 20.0f);
     else
@@ -507,9 +700,9 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
   {
     const int H4 = T / 16, WC = 4 * 512;
     if (h->bf16)
-      dsk::pool_time_kernel<true><<<B, 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC);
+      dsk::pool_time_kernel<true><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC);
     else
-      dsk::pool_time_kernel<false><<<B, 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC);
+      dsk::pool_time_kernel<false><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC);
     KERNEL_CHECK();
     mark();
     static bool fc_attr = false;
@@ -518,7 +711,7 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
       CUDA_TRY(cudaFuncSetAttribute(dsk::fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem));
       fc_attr = true;
     }
-    dim3 g((B + 7) / 8, h->emb / 64);
+    dim3 g((B + 7) / 8, h->emb / 8);
     dsk::fc_kernel<<<g, 256, fc_smem, s>>>(pl->pooled, h->fc_wq, h->fc_b, pl->fc_out, B, 2048, h->emb);
     KERNEL_CHECK();
     mark();
@@ -545,6 +738,298 @@ int32_t dsk_get_launch_times(dsk_handle h, float* ms_out, int32_t cap, int32_t* 
   if (n > 0) CUDA_TRY(cudaEventSynchronize(h->events[h->n_marks - 1]));
   for (int i = 0; i < n; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_out[i], h->events[i], h->events[i + 1]));
   *n_out = n;
+  return DSK_OK;
+}
+
+
+// ---- training ---------------------------------------------------------------------------------------------------
+static dsk::TransposeGeom make_geom(int N, int H, int W, int planes) {
+  dsk::TransposeGeom g;
+  g.H = H;
+  g.W = W;
+  g.planes = planes;
+  g.Hp = planes == 1 ? H : H / 2;
+  const int w = planes == 1 ? W : W / 2;
+  g.Wp = w < 8 ? 8 : w;
+  g.cstride = static_cast<long>(N) * planes * g.Hp * g.Wp;
+  g.dense = (planes == 1 && g.Wp == W) ? 1 : 0;
+  return g;
+}
+
+static int stat_blocks(long M, int C) {
+  long gx = kStatBlocksMax / (C / 64);
+  const long need = (M + 31) / 32;
+  if (gx > need) gx = need;
+  return gx < 1 ? 1 : static_cast<int>(gx);
+}
+
+static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
+  dsk_train_ctx_s* c = new dsk_train_ctx_s();
+  c->B = B;
+  c->T = T;
+  size_t bytes = 0;
+  auto take = [&](size_t n) {
+    const size_t o = bytes;
+    bytes += (n + 1023) / 1024 * 1024;
+    return o;
+  };
+  size_t o_raw[DSK_NUM_CONV], o_y[DSK_NUM_CONV], o_yT[DSK_NUM_CONV], o_mean[DSK_NUM_CONV], o_rstd[DSK_NUM_CONV];
+  size_t max_act = 0, max_gt = 0;
+  for (int i = 0; i < DSK_NUM_CONV; ++i) {
+    int H, W, C;
+    act_shape(i, T, H, W, C);
+    const size_t act = static_cast<size_t>(B) * H * W * C * 2;
+    if (act > max_act) max_act = act;
+    o_raw[i] = take(act);
+    o_y[i] = take(act);
+    c->tgG[i] = make_geom(B, H, W, 1);
+    const size_t gt = static_cast<size_t>(c->tgG[i].cstride) * C * 2;
+    if (gt > max_gt) max_gt = gt;
+    if (i < DSK_NUM_CONV - 1) {
+      const bool next_s2 = ((i + 1) % 3) == 0;
+      c->tgY[i] = make_geom(B, H, W, next_s2 ? 4 : 1);
+      o_yT[i] = take(static_cast<size_t>(c->tgY[i].cstride) * C * 2);
+    }
+    o_mean[i] = take(C * 4);
+    o_rstd[i] = take(C * 4);
+  }
+  const size_t o_pooled = take(static_cast<size_t>(B) * 2048 * 4), o_fc = take(static_cast<size_t>(B) * h->emb * 4);
+  const size_t o_inv = take(B * 4), o_sc = take(512 * 4), o_sh = take(512 * 4);
+  const size_t o_part = take(static_cast<size_t>(kStatBlocksMax) * 2 * 512 * 4), o_coef = take(3 * 512 * 4);
+  const size_t o_gfc = take(static_cast<size_t>(B) * h->emb * 4), o_dP = take(static_cast<size_t>(B) * 2048 * 4);
+  const size_t o_dw = take(static_cast<size_t>(25) * 512 * 256 * 4), o_c1 = take(static_cast<size_t>(1184) * 1600 * 4);
+  const size_t o_gA = take(max_act), o_gB = take(max_act), o_G = take(max_act), o_GT = take(max_gt), o_gres = take(max_act);
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->base), bytes));
+  CUDA_TRY(cudaMemset(c->base, 0, bytes));  // pad columns of the channel-major copies must stay zero
+  uint8_t* b = c->base;
+  for (int i = 0; i < DSK_NUM_CONV; ++i) {
+    c->raw[i] = b + o_raw[i];
+    c->y[i] = b + o_y[i];
+    c->yT[i] = i < DSK_NUM_CONV - 1 ? b + o_yT[i] : nullptr;
+    c->mean[i] = reinterpret_cast<float*>(b + o_mean[i]);
+    c->rstd[i] = reinterpret_cast<float*>(b + o_rstd[i]);
+  }
+  c->pooled = reinterpret_cast<float*>(b + o_pooled);
+  c->fc_out = reinterpret_cast<float*>(b + o_fc);
+  c->inv_norm = reinterpret_cast<float*>(b + o_inv);
+  c->scale_t = reinterpret_cast<float*>(b + o_sc);
+  c->shift_t = reinterpret_cast<float*>(b + o_sh);
+  c->partial = reinterpret_cast<float*>(b + o_part);
+  c->coef = reinterpret_cast<float*>(b + o_coef);
+  c->g_fc = reinterpret_cast<float*>(b + o_gfc);
+  c->dP = reinterpret_cast<float*>(b + o_dP);
+  c->dwacc = reinterpret_cast<float*>(b + o_dw);
+  c->c1part = reinterpret_cast<float*>(b + o_c1);
+  c->gA = b + o_gA;
+  c->gB = b + o_gB;
+  c->G = b + o_G;
+  c->GT = b + o_GT;
+  c->gt_bytes = max_gt;
+  c->gres = b + o_gres;
+  // launch descriptors
+  for (int i = 1; i < DSK_NUM_CONV; ++i) {
+    const LayerCfg lc = layer_cfg(i);
+    int Hi, Wi, Ci, Ho, Wo, Co;
+    act_shape(i - 1, T, Hi, Wi, Ci);
+    act_shape(i, T, Ho, Wo, Co);
+    int rc = build_conv(h, &c->conv[i], c->y[i - 1], h->wpk[i], nullptr, nullptr, nullptr, c->raw[i], B, Hi, Wi, lc.cin,
+                        lc.cout, lc.ksize, lc.stride, 0, 0.f);
+    if (rc) return rc;
+    // gradient w.r.t. y[i-1] lands in the buffer that is not holding the gradient w.r.t. y[i]
+    void* g_out = ((DSK_NUM_CONV - 1 - i) % 2 == 0) ? c->gB : c->gA;
+    if (lc.stride == 1) {
+      const void* res = (i % 3 == 1) ? c->gres : nullptr;  // skip connection joins at the block input
+      rc = build_dgrad_s1(h, &c->dgrad[i][0], c->G, h->wpk_dgrad[i], res, g_out, B, Ho, Wo, lc.cin, lc.cout);
+      c->n_dgrad[i] = 1;
+    } else {
+      for (int cls = 0; cls < 4 && !rc; ++cls)
+        rc = build_dgrad_s2(h, &c->dgrad[i][cls], c->G, h->wpk_dgrad[i], g_out, B, Ho, Wo, lc.cin, lc.cout, cls >> 1, cls & 1);
+      c->n_dgrad[i] = 4;
+    }
+    if (rc) return rc;
+    rc = build_wgrad(h, &c->wgrad[i], c->GT, c->yT[i - 1], B, Ho, c->tgG[i].Wp, c->tgY[i - 1].planes, lc.cout, lc.cin,
+                     lc.ksize, lc.stride, c->dwacc);
+    if (rc) return rc;
+  }
+  *out = c;
+  return DSK_OK;
+}
+
+int32_t dsk_set_loss_scale(dsk_handle h, float scale) {
+  if (!h) return fail(DSK_ERR_INVALID, "null handle");
+  if (scale < 0.f) return fail(DSK_ERR_INVALID, "loss scale must be >= 0 (0 = automatic)");
+  h->loss_scale = scale;
+  return DSK_OK;
+}
+
+static float effective_loss_scale(const dsk_handle_s* h, int B) {
+  if (h->loss_scale > 0.f) return h->loss_scale;
+  if (h->bf16) return 1.0f;
+  // fp16 gradients: activations' gradients scale like 1/B (mean over the batch); keep them near 2^-4 .. 2^4
+  int lg = 0;
+  while ((1 << (lg + 1)) <= B) ++lg;
+  int e = 9 + lg;
+  if (e > 16) e = 16;
+  return static_cast<float>(1 << e);
+}
+
+int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, dsk_train_ctx* ctx_out,
+                                 void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!h->weights_loaded) return fail(DSK_ERR_STATE, "dsk_rescnn_forward_train: call dsk_load_weights first");
+  if (!x || !emb || !ctx_out || B <= 0) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward_train: bad arguments");
+  if (T < 16 || T % 16) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward_train: T must be a positive multiple of 16 (got %d)", T);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dsk_train_ctx_s* c = nullptr;
+  for (dsk_train_ctx_s* cand : h->ctx_pool)
+    if (!cand->in_use && cand->B == B && cand->T == T) {
+      c = cand;
+      break;
+    }
+  if (!c) {
+    rc = ctx_create(h, B, T, &c);
+    if (rc) return rc;
+    h->ctx_pool.push_back(c);
+  }
+  c->in_use = true;
+  c->forward_done = false;
+  c->x = x;
+  const bool bf = h->bf16;
+  for (int i = 0; i < DSK_NUM_CONV; ++i) {
+    int H, W, C;
+    act_shape(i, T, H, W, C);
+    const long M = static_cast<long>(B) * H * W;
+    if (i == 0) {
+      const int blocks = B * ((T / 2 + 7) / 8);
+      if (bf) dsk::conv1_kernel<true><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->ones, h->zeros, (uint16_t*)c->raw[0], T, 0, 0.f);
+      else dsk::conv1_kernel<false><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->ones, h->zeros, (uint16_t*)c->raw[0], T, 0, 0.f);
+      KERNEL_CHECK();
+    } else {
+      rc = launch_conv(h, c->conv[i], s);
+      if (rc) return rc;
+    }
+    const int gx = stat_blocks(M, C);
+    dim3 gs(gx, C / 64);
+    if (bf) dsk::bn_stats_partial_kernel<true><<<gs, 256, 0, s>>>((const uint16_t*)c->raw[i], M, C, c->partial);
+    else dsk::bn_stats_partial_kernel<false><<<gs, 256, 0, s>>>((const uint16_t*)c->raw[i], M, C, c->partial);
+    KERNEL_CHECK();
+    dsk::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], h->w.bn_beta[i],
+                                                           h->w.bn_running_mean[i], h->w.bn_running_var[i], 0.1f, 1e-5f,
+                                                           c->mean[i], c->rstd[i], c->scale_t, c->shift_t);
+    KERNEL_CHECK();
+    const uint16_t* res = (i % 3 == 2) ? (const uint16_t*)c->y[i - 2] : nullptr;
+    dim3 ga(static_cast<unsigned>((M + 63) / 64), C / 64);
+    if (bf)
+      dsk::bn_apply_kernel<true><<<ga, 256, 0, s>>>((const uint16_t*)c->raw[i], c->scale_t, c->shift_t, res, (uint16_t*)c->y[i],
+                                                    (uint16_t*)c->yT[i], M, C, 20.0f, c->tgY[i]);
+    else
+      dsk::bn_apply_kernel<false><<<ga, 256, 0, s>>>((const uint16_t*)c->raw[i], c->scale_t, c->shift_t, res, (uint16_t*)c->y[i],
+                                                     (uint16_t*)c->yT[i], M, C, 20.0f, c->tgY[i]);
+    KERNEL_CHECK();
+  }
+  {
+    const int H4 = T / 16, WC = 4 * 512;
+    if (bf) dsk::pool_time_kernel<true><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC);
+    else dsk::pool_time_kernel<false><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC);
+    KERNEL_CHECK();
+    const int fc_smem = 8 * 2048 * 4;
+    CUDA_TRY(cudaFuncSetAttribute(dsk::fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem));
+    dim3 g((B + 7) / 8, h->emb / 8);
+    dsk::fc_kernel<<<g, 256, fc_smem, s>>>(c->pooled, h->fc_wq, h->fc_b, c->fc_out, B, 2048, h->emb);
+    KERNEL_CHECK();
+    dsk::l2norm_kernel<<<B, 128, 0, s>>>(c->fc_out, emb, c->inv_norm, h->emb, 10.0f);
+    KERNEL_CHECK();
+  }
+  c->forward_done = true;
+  *ctx_out = c;
+  return DSK_OK;
+}
+
+int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb, const dsk_grads* g, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!c || !c->in_use || !c->forward_done) return fail(DSK_ERR_STATE, "dsk_rescnn_backward: context has no pending forward");
+  if (!grad_emb || !g) return fail(DSK_ERR_INVALID, "dsk_rescnn_backward: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool bf = h->bf16;
+  const int B = c->B, T = c->T, E = h->emb;
+  const float S = effective_loss_scale(h, B);
+  const float invS = 1.0f / S;
+  // tail
+  dsk::l2norm_bwd_kernel<<<B, 128, 0, s>>>(c->fc_out, c->inv_norm, grad_emb, c->g_fc, E, 10.0f);
+  KERNEL_CHECK();
+  dsk::fc_bwd_weight_kernel<<<dim3(E / 8, 2048 / 256), 256, 0, s>>>(c->g_fc, c->pooled, g->fc_w, g->fc_b, B, 2048, E, 512, 4);
+  KERNEL_CHECK();
+  dsk::fc_bwd_input_kernel<<<dim3(B, 2048 / 256), 256, E * 4, s>>>(c->g_fc, h->fc_wq, c->dP, 2048, E);
+  KERNEL_CHECK();
+  {
+    const int H4 = T / 16;
+    if (bf) dsk::pool_bwd_kernel<true><<<B, 256, 0, s>>>(c->dP, (uint16_t*)c->gA, H4, 2048, S / H4);
+    else dsk::pool_bwd_kernel<false><<<B, 256, 0, s>>>(c->dP, (uint16_t*)c->gA, H4, 2048, S / H4);
+    KERNEL_CHECK();
+  }
+  CUDA_TRY(cudaMemsetAsync(c->GT, 0, c->gt_bytes, s));  // zero pad columns for the padded stage-4 geometry
+  for (int i = DSK_NUM_CONV - 1; i >= 0; --i) {
+    int H, W, C;
+    act_shape(i, T, H, W, C);
+    const long M = static_cast<long>(B) * H * W;
+    const uint16_t* gy = (const uint16_t*)(((DSK_NUM_CONV - 1 - i) % 2 == 0) ? c->gA : c->gB);
+    const int gx = stat_blocks(M, C);
+    dim3 gs(gx, C / 64);
+    if (bf)
+      dsk::bn_bwd_reduce_kernel<true><<<gs, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], (const uint16_t*)c->raw[i], c->mean[i],
+                                                         c->rstd[i], M, C, 20.0f, c->partial);
+    else
+      dsk::bn_bwd_reduce_kernel<false><<<gs, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], (const uint16_t*)c->raw[i], c->mean[i],
+                                                          c->rstd[i], M, C, 20.0f, c->partial);
+    KERNEL_CHECK();
+    dsk::bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], c->rstd[i], invS,
+                                                               g->bn_gamma[i], g->bn_beta[i], c->coef);
+    KERNEL_CHECK();
+    uint16_t* gres = (i % 3 == 2) ? (uint16_t*)c->gres : nullptr;
+    dim3 ga(static_cast<unsigned>((M + 63) / 64), C / 64);
+    if (bf)
+      dsk::bn_bwd_apply_kernel<true><<<ga, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], (const uint16_t*)c->raw[i], c->mean[i],
+                                                        c->rstd[i], c->coef, (uint16_t*)c->G, (uint16_t*)c->GT, gres, M, C,
+                                                        20.0f, c->tgG[i]);
+    else
+      dsk::bn_bwd_apply_kernel<false><<<ga, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], (const uint16_t*)c->raw[i], c->mean[i],
+                                                         c->rstd[i], c->coef, (uint16_t*)c->G, (uint16_t*)c->GT, gres, M, C,
+                                                         20.0f, c->tgG[i]);
+    KERNEL_CHECK();
+    const LayerCfg lc = layer_cfg(i);
+    if (i == 0) {
+      const int nblk = 1184;
+      if (bf) dsk::conv1_wgrad_partial_kernel<true><<<nblk, 256, 0, s>>>((const uint16_t*)c->G, c->x, B, T, c->c1part);
+      else dsk::conv1_wgrad_partial_kernel<false><<<nblk, 256, 0, s>>>((const uint16_t*)c->G, c->x, B, T, c->c1part);
+      KERNEL_CHECK();
+      dsk::sum_partials_kernel<<<(1600 + 127) / 128, 128, 0, s>>>(c->c1part, nblk, 1600, invS, g->conv_w[0]);
+      KERNEL_CHECK();
+    } else {
+      const int taps = lc.ksize * lc.ksize;
+      const size_t n = static_cast<size_t>(taps) * lc.cout * lc.cin;
+      CUDA_TRY(cudaMemsetAsync(c->dwacc, 0, n * 4, s));
+      rc = launch_wgrad(h, c->wgrad[i], s);
+      if (rc) return rc;
+      dsk::unpack_wgrad_kernel<<<static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, s>>>(
+          c->dwacc, g->conv_w[i], lc.cout, lc.cin, taps, invS);
+      KERNEL_CHECK();
+      for (int k = 0; k < c->n_dgrad[i]; ++k) {
+        rc = launch_conv(h, c->dgrad[i][k], s);
+        if (rc) return rc;
+      }
+    }
+  }
+  c->forward_done = false;
+  c->in_use = false;
+  return DSK_OK;
+}
+
+int32_t dsk_train_ctx_release(dsk_handle h, dsk_train_ctx c) {
+  if (!h || !c) return fail(DSK_ERR_INVALID, "dsk_train_ctx_release: null argument");
+  c->in_use = false;
+  c->forward_done = false;
   return DSK_OK;
 }
 

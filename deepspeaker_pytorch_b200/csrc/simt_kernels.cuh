@@ -22,11 +22,12 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, uint16_t* _
   }
 }
 
-// Same but with the filter rotated by 180 degrees and cin/cout swapped: the weight of the
-// "data-gradient as a convolution" of a stride-1 conv. out[tap'][ci][co] = w[co][ci][taps-1-tap'].
+// Same with cin/cout swapped (the weight of "data-gradient as a convolution"): out[tap'][ci][co] =
+// w[co][ci][rotate ? taps-1-tap' : tap'].  rotate=1 (filter turned by 180 degrees) for stride-1 convs; the
+// stride-2 data-gradient picks its taps by index and keeps the original order.
 template <bool BF16>
 __global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int cout,
-                                              int cin, int taps) {
+                                              int cin, int taps, int rotate) {
   const long total = static_cast<long>(cout) * cin * taps;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -34,7 +35,7 @@ __global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, uint1
     const long r = i / cout;
     const int ci = r % cin;
     const int tap = r / cin;
-    out[i] = to16<BF16>(w[(static_cast<long>(co) * cin + ci) * taps + (taps - 1 - tap)]);
+    out[i] = to16<BF16>(w[(static_cast<long>(co) * cin + ci) * taps + (rotate ? taps - 1 - tap : tap)]);
   }
 }
 
@@ -61,8 +62,9 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]*/, const float* __restrict__ scale,
              const float* __restrict__ bias, uint16_t* __restrict__ out, int T, int do_clip, float clip_hi) {
-  constexpr int WIN = 64, WOUT = 32, ROWS = 4, PATCH_ROWS = 2 * ROWS + 3, PATCH_W = WIN + 4;
+  constexpr int WIN = 64, WOUT = 32, ROWS = 8, PATCH_ROWS = 2 * ROWS + 3, PATCH_W = WIN + 4;
   __shared__ float patch[PATCH_ROWS][PATCH_W];
+  __shared__ float wsm[64 * 25];
   const int hout = T / 2;
   const int tiles_h = (hout + ROWS - 1) / ROWS;
   const int n = blockIdx.x / tiles_h;
@@ -73,28 +75,29 @@ conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]
     const int ih = 2 * h0 - 2 + pr, iw = pc - 2;
     patch[pr][pc] = (ih >= 0 && ih < T && iw >= 0 && iw < WIN) ? xin[ih * WIN + iw] : 0.0f;
   }
+  for (int i = threadIdx.x; i < 64 * 25; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = lane * 2;
   float w0[25], w1[25];
 #pragma unroll
   for (int t = 0; t < 25; ++t) {
-    w0[t] = w[c0 * 25 + t];
-    w1[t] = w[(c0 + 1) * 25 + t];
+    w0[t] = wsm[c0 * 25 + t];
+    w1[t] = wsm[(c0 + 1) * 25 + t];
   }
   const float s0 = scale[c0], s1 = scale[c0 + 1], b0 = bias[c0], b1 = bias[c0 + 1];
-  __syncthreads();
   uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
-  for (int pi = 0; pi < 16; ++pi) {
-    const int p = warp * 16 + pi;  // 0..127 = 4 rows x 32 cols
-    const int lh = p >> 5, ow = p & 31;
-    const int oh = h0 + lh;
-    if (oh >= hout) break;
+  const int oh = h0 + warp;  // one output row per warp
+  if (oh >= hout) return;
+  const long pix0 = (static_cast<long>(n) * hout + oh) * WOUT;
+#pragma unroll 2
+  for (int ow = 0; ow < WOUT; ++ow) {
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
 #pragma unroll
       for (int s = 0; s < 5; ++s) {
-        const float v = patch[2 * lh + r][2 * ow + s];
+        const float v = patch[2 * warp + r][2 * ow + s];
         a0 = fmaf(v, w0[r * 5 + s], a0);
         a1 = fmaf(v, w1[r * 5 + s], a1);
       }
@@ -105,8 +108,7 @@ conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]
       a0 = fminf(fmaxf(a0, 0.f), clip_hi);
       a1 = fminf(fmaxf(a1, 0.f), clip_hi);
     }
-    const long pix = (static_cast<long>(n) * hout + oh) * WOUT + ow;
-    o32[pix * 32 + lane] = pack2<BF16>(a0, a1);
+    o32[(pix0 + ow) * 32 + lane] = pack2<BF16>(a0, a1);
   }
 }
 
@@ -117,21 +119,34 @@ conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]
 // The fc weight is repacked once to the same (w, c) column order: wq[e][w*C + c] = W[e][c*4 + w].
 // ---------------------------------------------------------------------------------------------
 template <bool BF16>
-__global__ void pool_time_kernel(const uint16_t* __restrict__ act, float* __restrict__ pooled, int H, int WC) {
-  // grid (B), block 256; each thread 2 adjacent elements per step (32-bit loads)
+__global__ void __launch_bounds__(256)
+pool_time_kernel(const uint16_t* __restrict__ act, float* __restrict__ pooled, int H, int WC) {
+  // grid (B, WC/512): thread = 2 adjacent channels (one 32-bit load per time step), loads independent in h
   const int b = blockIdx.x;
-  const uint32_t* a = reinterpret_cast<const uint32_t*>(act + static_cast<long>(b) * H * WC);
+  const int i = blockIdx.y * 256 + threadIdx.x;  // index of the channel pair
+  if (i >= WC / 2) return;
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(act + static_cast<long>(b) * H * WC) + i;
   const float inv = 1.0f / static_cast<float>(H);
-  for (int i = threadIdx.x; i < WC / 2; i += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f;
-    for (int h = 0; h < H; ++h) {
-      const float2 v = unpack2<BF16>(a[h * (WC / 2) + i]);
+  float s0 = 0.f, s1 = 0.f;
+  int h = 0;
+  for (; h + 4 <= H; h += 4) {
+    uint32_t u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = a[static_cast<long>(h + j) * (WC / 2)];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 v = unpack2<BF16>(u[j]);
       s0 += v.x;
       s1 += v.y;
     }
-    pooled[static_cast<long>(b) * WC + 2 * i] = s0 * inv;
-    pooled[static_cast<long>(b) * WC + 2 * i + 1] = s1 * inv;
   }
+  for (; h < H; ++h) {
+    const float2 v = unpack2<BF16>(a[static_cast<long>(h) * (WC / 2)]);
+    s0 += v.x;
+    s1 += v.y;
+  }
+  pooled[static_cast<long>(b) * WC + 2 * i] = s0 * inv;
+  pooled[static_cast<long>(b) * WC + 2 * i + 1] = s1 * inv;
 }
 
 __global__ void pack_fc_weight_kernel(const float* __restrict__ w /*[E][C*4+w]*/, float* __restrict__ out, int E,
@@ -147,42 +162,61 @@ __global__ void pack_fc_weight_kernel(const float* __restrict__ w /*[E][C*4+w]*/
   }
 }
 
-// y[b][e] = sum_k pooled[b][k] * wq[e][k] + bias[e].  grid (ceil(B/8), E/64), block 256.
+// y[b][e] = sum_k pooled[b][k] * wq[e][k] + bias[e].  grid (ceil(B/8), E/8), block 256 = 8 warps.
+// Warp = one output feature e for 8 utterances: the 8 KB weight row is read once, coalesced (512 B per
+// instruction, 4 independent loads in flight); the 8 pooled vectors sit in shared memory.
 __global__ void __launch_bounds__(256)
 fc_kernel(const float* __restrict__ pooled, const float* __restrict__ wq, const float* __restrict__ bias,
           float* __restrict__ y, int B, int K, int E) {
   constexpr int UT = 8;
   extern __shared__ float sp[];  // [UT][K]
   const int b0 = blockIdx.x * UT;
-  const int e0 = blockIdx.y * 64;
-  for (int i = threadIdx.x; i < UT * K; i += blockDim.x) {
-    const int u = i / K;
-    sp[i] = (b0 + u < B) ? pooled[static_cast<long>(b0 + u) * K + (i - u * K)] : 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.y * 8 + warp;
+  const float4* wr = reinterpret_cast<const float4*>(wq + static_cast<long>(e) * K);
+  const int n4 = K / 4;
+  // issue the first weight loads before the shared-memory fill so their latency overlaps it
+  float4 wv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wv[j] = wr[j * 32 + lane];
+  for (int i = threadIdx.x; i < UT * n4; i += blockDim.x) {
+    const int u = i / n4;
+    reinterpret_cast<float4*>(sp)[i] = (b0 + u < B)
+        ? reinterpret_cast<const float4*>(pooled + static_cast<long>(b0 + u) * K)[i - u * n4]
+        : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  const int e = e0 + (threadIdx.x >> 2);
-  const int part = threadIdx.x & 3;
-  const float4* wr = reinterpret_cast<const float4*>(wq + static_cast<long>(e) * K);
   float acc[UT];
 #pragma unroll
   for (int u = 0; u < UT; ++u) acc[u] = 0.f;
-  for (int i = part; i < K / 4; i += 4) {
-    const float4 wv = wr[i];
+  for (int i0 = 0; i0 < n4; i0 += 128) {
+    float4 nx[4];
+    const bool more = i0 + 128 < n4;
+    if (more) {
 #pragma unroll
-    for (int u = 0; u < UT; ++u) {
-      const float4 pv = reinterpret_cast<const float4*>(sp + u * K)[i];
-      acc[u] = fmaf(wv.x, pv.x, acc[u]);
-      acc[u] = fmaf(wv.y, pv.y, acc[u]);
-      acc[u] = fmaf(wv.z, pv.z, acc[u]);
-      acc[u] = fmaf(wv.w, pv.w, acc[u]);
+      for (int j = 0; j < 4; ++j) nx[j] = wr[i0 + 128 + j * 32 + lane];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * 32 + lane;
+#pragma unroll
+      for (int u = 0; u < UT; ++u) {
+        const float4 pv = reinterpret_cast<const float4*>(sp + u * K)[i];
+        acc[u] = fmaf(wv[j].x, pv.x, acc[u]);
+        acc[u] = fmaf(wv[j].y, pv.y, acc[u]);
+        acc[u] = fmaf(wv[j].z, pv.z, acc[u]);
+        acc[u] = fmaf(wv[j].w, pv.w, acc[u]);
+      }
+    }
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[j] = nx[j];
     }
   }
 #pragma unroll
-  for (int u = 0; u < UT; ++u) {
-    acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], 1);
-    acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], 2);
-  }
-  if (part == 0) {
+  for (int u = 0; u < UT; ++u)
+    for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+  if (lane == 0) {
     const float bb = bias[e];
 #pragma unroll
     for (int u = 0; u < UT; ++u)

@@ -33,3 +33,443 @@ __global__ void nhwc16_to_nchw_kernel(const uint16_t* __restrict__ in, float* __
 }
 
 }  // namespace dsk
+
+// =================================================================================================
+// Training mode.  BatchNorm2d with batch statistics (/root/reference/model.py:59,62,94,99,103,107 in
+// train mode, called once per a/p/n forward: train_triplet.py:215) and the backward of every non-conv op.
+//
+// Elementwise kernels work on tiles of 64 pixels x 64 channels of an NHWC 16-bit tensor viewed as
+// [M pixels][C]; thread t handles pixels {t/8, t/8+32} and the 8 channels (16 bytes) t%8 of the chunk.
+// Reductions are two-stage and deterministic: per-block partials, then a fixed-order finalize.
+// =================================================================================================
+namespace dsk {
+
+constexpr int kEwTilePix = 64;
+
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack2<BF16>(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack2<BF16>(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack2<BF16>(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack2<BF16>(u.w); f[6] = t.x; f[7] = t.y;
+}
+template <bool BF16>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack2<BF16>(f[0], f[1]);
+  o.y = pack2<BF16>(f[2], f[3]);
+  o.z = pack2<BF16>(f[4], f[5]);
+  o.w = pack2<BF16>(f[6], f[7]);
+  return o;
+}
+
+// Where pixel m = (n, h, w) of a [N][H][W] grid lands in the channel-major ("transposed") copy used by the
+// weight-gradient GEMM: [c][n][plane][Hp][Wp].  planes == 1: plain image rows (Hp = H).  planes == 4: parity
+// planes for a stride-2 consumer (plane = (h&1)*2 + (w&1), Hp = H/2).  Wp >= row width is the padded row
+// pitch (TMA needs rows of >= 16 bytes); pad columns are zero and never written.
+struct TransposeGeom {
+  int H, W;      // pixel grid of the tensor
+  int planes;    // 1 or 4
+  int Hp, Wp;    // rows / row pitch inside one plane
+  long cstride;  // elements per channel = N * planes * Hp * Wp
+  int dense;     // 1 if position == m (planes == 1 and Wp == W): enables the vectorised path
+};
+__device__ __forceinline__ long tpos(const TransposeGeom& g, long m) {
+  const int w = m % g.W;
+  const long r = m / g.W;
+  const int h = r % g.H;
+  const long n = r / g.H;
+  if (g.planes == 1) return (n * g.Hp + h) * g.Wp + w;
+  return ((n * 4 + (h & 1) * 2 + (w & 1)) * g.Hp + (h >> 1)) * static_cast<long>(g.Wp) + (w >> 1);
+}
+
+// ---- forward: per-channel sum / sum of squares of the raw conv output --------------------------------------
+// grid (gx, C/64); partial[(bx*2 + stat)*C + c]
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+bn_stats_partial_kernel(const uint16_t* __restrict__ raw, long M, int C, float* __restrict__ partial) {
+  __shared__ float red[2][32][65];
+  const int q = threadIdx.x & 7, p = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * 64 + q * 8;
+  float s[8], ss[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
+  for (long m = blockIdx.x * 32L + p; m < M; m += 32L * gridDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(raw + m * C + c0);
+    float f[8];
+    unpack8<BF16>(u, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s[e] += f[e];
+      ss[e] = fmaf(f[e], f[e], ss[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][p][q * 8 + e] = s[e];
+    red[1][p][q * 8 + e] = ss[e];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int stat = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += red[stat][i][c];
+    partial[(static_cast<long>(blockIdx.x) * 2 + stat) * C + blockIdx.y * 64 + c] = t;
+  }
+}
+
+// mean / biased var -> rstd, scale = gamma*rstd, shift = beta - mean*scale; running stats (momentum, unbiased var)
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long M,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                   float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += partial[(static_cast<long>(b) * 2) * C + c];
+    ss += partial[(static_cast<long>(b) * 2 + 1) * C + c];
+  }
+  const double mean = s / static_cast<double>(M);
+  double var = ss / static_cast<double>(M) - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[c] * rstd;
+  mean_out[c] = static_cast<float>(mean);
+  rstd_out[c] = rstd;
+  scale_out[c] = sc;
+  shift_out[c] = beta[c] - static_cast<float>(mean) * sc;
+  const double unbiased = M > 1 ? var * static_cast<double>(M) / static_cast<double>(M - 1) : var;
+  running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+  running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+}
+
+// ---- forward: y = clip(raw*scale + shift (+res), 0, hi) -> NHWC y and channel-major copy yT ------------------
+// grid (ceil(M/64), C/64)
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
+                const uint16_t* __restrict__ res, uint16_t* __restrict__ y, uint16_t* __restrict__ yT, long M, int C,
+                float clip_hi, TransposeGeom tg) {
+  __shared__ uint16_t tile[64][kEwTilePix + 8];
+  const int q = threadIdx.x & 7, p = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * 64 + q * 8;
+  const long m0 = static_cast<long>(blockIdx.x) * kEwTilePix;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = scale[c0 + e];
+    sh[e] = shift[c0 + e];
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int lp = p + 32 * half;
+    const long m = m0 + lp;
+    float f[8];
+    if (m < M) {
+      unpack8<BF16>(*reinterpret_cast<const uint4*>(raw + m * C + c0), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+      if (res) {
+        float r[8];
+        unpack8<BF16>(*reinterpret_cast<const uint4*>(res + m * C + c0), r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += r[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], 0.f), clip_hi);
+      const uint4 o = pack8<BF16>(f);
+      *reinterpret_cast<uint4*>(y + m * C + c0) = o;
+      if (yT) {
+        const uint16_t* h16 = reinterpret_cast<const uint16_t*>(&o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tile[q * 8 + e][lp] = h16[e];
+      }
+    }
+  }
+  if (!yT) return;
+  __syncthreads();
+  // channel-major write: thread -> (channel = t/4, 16 pixels = t%4)
+  const int ch = threadIdx.x >> 2, seg = threadIdx.x & 3;
+  uint16_t* dst = yT + static_cast<long>(blockIdx.y * 64 + ch) * tg.cstride;
+  if (tg.dense && m0 + kEwTilePix <= M) {
+    const uint4* src = reinterpret_cast<const uint4*>(&tile[ch][seg * 16]);
+    uint4* d = reinterpret_cast<uint4*>(dst + m0 + seg * 16);
+    d[0] = src[0];
+    d[1] = src[1];
+  } else {
+    for (int i = 0; i < 16; ++i) {
+      const long m = m0 + seg * 16 + i;
+      if (m < M) dst[tpos(tg, m)] = tile[ch][seg * 16 + i];
+    }
+  }
+}
+
+// ---- backward: dbeta = sum g_z, dgamma = sum g_z * xhat, with g_z = g_y * 1[0 < y < hi] -----------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const uint16_t* __restrict__ gy, const uint16_t* __restrict__ y, const uint16_t* __restrict__ raw,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, long M, int C, float clip_hi,
+                     float* __restrict__ partial) {
+  __shared__ float red[2][32][65];
+  const int q = threadIdx.x & 7, p = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * 64 + q * 8;
+  float mu[8], rs[8], s[8], ss[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mu[e] = mean[c0 + e];
+    rs[e] = rstd[c0 + e];
+    s[e] = ss[e] = 0.f;
+  }
+  for (long m = blockIdx.x * 32L + p; m < M; m += 32L * gridDim.x) {
+    float g[8], yy[8], r[8];
+    unpack8<BF16>(*reinterpret_cast<const uint4*>(gy + m * C + c0), g);
+    unpack8<BF16>(*reinterpret_cast<const uint4*>(y + m * C + c0), yy);
+    unpack8<BF16>(*reinterpret_cast<const uint4*>(raw + m * C + c0), r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gz = (yy[e] > 0.f && yy[e] < clip_hi) ? g[e] : 0.f;
+      s[e] += gz;
+      ss[e] = fmaf(gz, (r[e] - mu[e]) * rs[e], ss[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][p][q * 8 + e] = s[e];
+    red[1][p][q * 8 + e] = ss[e];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int stat = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += red[stat][i][c];
+    partial[(static_cast<long>(blockIdx.x) * 2 + stat) * C + blockIdx.y * 64 + c] = t;
+  }
+}
+
+// dgamma, dbeta (unscaled by 1/S) and the three per-channel coefficients of
+// g_raw = a * (g_z - b - xhat * d),  a = gamma*rstd, b = dbeta/M, d = dgamma/M.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long M,
+                                       const float* __restrict__ gamma, const float* __restrict__ rstd,
+                                       float inv_loss_scale, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ coef /*[3][C]*/) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += partial[(static_cast<long>(b) * 2) * C + c];
+    ss += partial[(static_cast<long>(b) * 2 + 1) * C + c];
+  }
+  dbeta[c] = static_cast<float>(s) * inv_loss_scale;
+  dgamma[c] = static_cast<float>(ss) * inv_loss_scale;
+  coef[c] = gamma[c] * rstd[c];
+  coef[C + c] = static_cast<float>(s / static_cast<double>(M));
+  coef[2 * C + c] = static_cast<float>(ss / static_cast<double>(M));
+}
+
+// g_raw -> G (NHWC) and GT (channel-major, plain layout); optionally g_z -> gres (NHWC) for the skip branch.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const uint16_t* __restrict__ gy, const uint16_t* __restrict__ y, const uint16_t* __restrict__ raw,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ coef,
+                    uint16_t* __restrict__ G, uint16_t* __restrict__ GT, uint16_t* __restrict__ gres, long M, int C,
+                    float clip_hi, TransposeGeom tg) {
+  __shared__ uint16_t tile[64][kEwTilePix + 8];
+  const int q = threadIdx.x & 7, p = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * 64 + q * 8;
+  const long m0 = static_cast<long>(blockIdx.x) * kEwTilePix;
+  float mu[8], rs[8], ca[8], cb[8], cd[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mu[e] = mean[c0 + e];
+    rs[e] = rstd[c0 + e];
+    ca[e] = coef[c0 + e];
+    cb[e] = coef[C + c0 + e];
+    cd[e] = coef[2 * C + c0 + e];
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int lp = p + 32 * half;
+    const long m = m0 + lp;
+    if (m < M) {
+      float g[8], yy[8], r[8];
+      unpack8<BF16>(*reinterpret_cast<const uint4*>(gy + m * C + c0), g);
+      unpack8<BF16>(*reinterpret_cast<const uint4*>(y + m * C + c0), yy);
+      unpack8<BF16>(*reinterpret_cast<const uint4*>(raw + m * C + c0), r);
+      float gz[8], gr[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        gz[e] = (yy[e] > 0.f && yy[e] < clip_hi) ? g[e] : 0.f;
+        gr[e] = ca[e] * (gz[e] - cb[e] - (r[e] - mu[e]) * rs[e] * cd[e]);
+      }
+      const uint4 o = pack8<BF16>(gr);
+      *reinterpret_cast<uint4*>(G + m * C + c0) = o;
+      if (gres) *reinterpret_cast<uint4*>(gres + m * C + c0) = pack8<BF16>(gz);
+      const uint16_t* h16 = reinterpret_cast<const uint16_t*>(&o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tile[q * 8 + e][lp] = h16[e];
+    }
+  }
+  __syncthreads();
+  const int ch = threadIdx.x >> 2, seg = threadIdx.x & 3;
+  uint16_t* dst = GT + static_cast<long>(blockIdx.y * 64 + ch) * tg.cstride;
+  if (tg.dense && m0 + kEwTilePix <= M) {
+    const uint4* src = reinterpret_cast<const uint4*>(&tile[ch][seg * 16]);
+    uint4* d = reinterpret_cast<uint4*>(dst + m0 + seg * 16);
+    d[0] = src[0];
+    d[1] = src[1];
+  } else {
+    for (int i = 0; i < 16; ++i) {
+      const long m = m0 + seg * 16 + i;
+      if (m < M) dst[tpos(tg, m)] = tile[ch][seg * 16 + i];
+    }
+  }
+}
+
+// ---- tail backward ---------------------------------------------------------------------------------------------
+// emb = alpha * x / sqrt(sum x^2 + 1e-10)  =>  g_x = alpha*inv * (g - xhat * (xhat . g)), xhat = x*inv.
+__global__ void l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ inv_norm,
+                                  const float* __restrict__ g, float* __restrict__ gx, int E, float alpha) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float inv = inv_norm[b];
+  const float* xr = x + static_cast<long>(b) * E;
+  const float* gr = g + static_cast<long>(b) * E;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) s = fmaf(xr[i] * inv, gr[i], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float dot = red[0];
+  for (int i = threadIdx.x; i < E; i += blockDim.x)
+    gx[static_cast<long>(b) * E + i] = alpha * inv * (gr[i] - xr[i] * inv * dot);
+}
+
+// dW[e][c*4+w] = sum_b gy[b][e] * pooled[b][w*512+c]  (written in the PyTorch fc.weight layout), db[e] = sum_b gy[b][e].
+// grid (E/8, K/256), block 256: thread = one k, 8 e's.
+__global__ void __launch_bounds__(256)
+fc_bwd_weight_kernel(const float* __restrict__ gy, const float* __restrict__ pooled, float* __restrict__ dW,
+                     float* __restrict__ db, int B, int K, int E, int Cch, int Wd) {
+  const int e0 = blockIdx.x * 8;
+  const int k = blockIdx.y * 256 + threadIdx.x;  // index in (w, c) order
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  float bsum = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float pv = pooled[static_cast<long>(b) * K + k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(gy[static_cast<long>(b) * E + e0 + j], pv, acc[j]);
+    if (blockIdx.y == 0 && threadIdx.x < 8) bsum += gy[static_cast<long>(b) * E + e0 + threadIdx.x];
+  }
+  const int wi = k / Cch, c = k % Cch;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dW[static_cast<long>(e0 + j) * K + c * Wd + wi] = acc[j];
+  if (blockIdx.y == 0 && threadIdx.x < 8) db[e0 + threadIdx.x] = bsum;
+}
+
+// dP[b][k] = sum_e gy[b][e] * wq[e][k]   grid (B, K/256)
+__global__ void __launch_bounds__(256)
+fc_bwd_input_kernel(const float* __restrict__ gy, const float* __restrict__ wq, float* __restrict__ dP, int K, int E) {
+  extern __shared__ float sg[];  // [E]
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) sg[i] = gy[static_cast<long>(b) * E + i];
+  __syncthreads();
+  const int k = blockIdx.y * 256 + threadIdx.x;
+  float acc = 0.f;
+  for (int e = 0; e < E; ++e) acc = fmaf(sg[e], wq[static_cast<long>(e) * K + k], acc);
+  dP[static_cast<long>(b) * K + k] = acc;
+}
+
+// g_y[b][h][w][c] = loss_scale * dP[b][w*C + c] / H  (mean over time backward) -> 16-bit NHWC
+template <bool BF16>
+__global__ void pool_bwd_kernel(const float* __restrict__ dP, uint16_t* __restrict__ gy, int H, int WC, float mult) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < WC; i += blockDim.x) {
+    const uint16_t v = to16<BF16>(dP[static_cast<long>(b) * WC + i] * mult);
+    for (int h = 0; h < H; ++h) gy[(static_cast<long>(b) * H + h) * WC + i] = v;
+  }
+}
+
+// ---- conv1 weight gradient (Cin = 1): dW[co][r][s] = sum_pix G[pix][co] * x[2h-2+r][2w-2+s] -----------------------
+// grid (nblk), block 256 = 8 warps; warp handles pixels, lane = 2 output channels; 25 taps x 2 accumulators.
+// partial[blk][co][25]; finalized by conv1_wgrad_finalize_kernel.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+conv1_wgrad_partial_kernel(const uint16_t* __restrict__ G, const float* __restrict__ x, int B, int T,
+                           float* __restrict__ partial) {
+  __shared__ float red[64 * 25];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 64 * 25; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int hout = T / 2;
+  const long npix = static_cast<long>(B) * hout * 32;
+  float a0[25], a1[25];
+#pragma unroll
+  for (int t = 0; t < 25; ++t) a0[t] = a1[t] = 0.f;
+  const uint32_t* g32 = reinterpret_cast<const uint32_t*>(G);
+  for (long pix = blockIdx.x * 8L + warp; pix < npix; pix += 8L * gridDim.x) {
+    const int ow = pix & 31;
+    const long r = pix >> 5;
+    const int oh = r % hout;
+    const long n = r / hout;
+    const float2 g = unpack2<BF16>(g32[pix * 32 + lane]);
+    const float* xin = x + n * T * 64;
+#pragma unroll
+    for (int rr = 0; rr < 5; ++rr) {
+      const int ih = 2 * oh - 2 + rr;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        const int iw = 2 * ow - 2 + s;
+        const float v = (ih >= 0 && ih < T && iw >= 0 && iw < 64) ? xin[ih * 64 + iw] : 0.f;
+        a0[rr * 5 + s] = fmaf(g.x, v, a0[rr * 5 + s]);
+        a1[rr * 5 + s] = fmaf(g.y, v, a1[rr * 5 + s]);
+      }
+    }
+  }
+  // warp w adds in round w so the shared-memory sum has a fixed order (deterministic)
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int t = 0; t < 25; ++t) {
+        red[(lane * 2) * 25 + t] += a0[t];
+        red[(lane * 2 + 1) * 25 + t] += a1[t];
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < 64 * 25; i += blockDim.x) partial[static_cast<long>(blockIdx.x) * 1600 + i] = red[i];
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int nblk, int n, float mult,
+                                    float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double t = 0.0;
+  for (int b = 0; b < nblk; ++b) t += partial[static_cast<long>(b) * n + i];
+  out[i] = static_cast<float>(t) * mult;
+}
+
+// dW fp32 [tap][co][ci] (accumulated by the wgrad GEMM) -> OIHW [co][ci][tap] scaled by mult.
+__global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restrict__ out, int cout, int cin, int taps,
+                                    float mult) {
+  const long total = static_cast<long>(cout) * cin * taps;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int tap = i % taps;
+    const long r = i / taps;
+    const int ci = r % cin;
+    const int co = r / cin;
+    out[i] = in[(static_cast<long>(tap) * cout + co) * cin + ci] * mult;
+  }
+}
+
+}  // namespace dsk

@@ -43,6 +43,11 @@ class Engine:
                                     L.DSK_BF16 if operand_dtype == "bf16" else L.DSK_F16), "dsk_create")
         self._versions = None
         self._wstruct = None
+        self.train_calls = 0  # train-mode forwards update BN running stats through raw pointers
+
+    def set_loss_scale(self, scale: float):
+        """fp16 gradient scale used inside the backward (0 = automatic, see include/dsk.h)."""
+        L.check(self.lib.dsk_set_loss_scale(self.handle, float(scale)), "dsk_set_loss_scale")
 
     def __del__(self):
         try:
@@ -61,7 +66,8 @@ class Engine:
             if eval_mode:
                 vs += [bn.running_mean._version, bn.running_var._version]
         fc = m.model.fc
-        vs += [fc.weight._version, fc.bias._version, fc.weight.data_ptr(), int(eval_mode)]
+        vs += [fc.weight._version, fc.bias._version, fc.weight.data_ptr(), int(eval_mode),
+               self.train_calls if eval_mode else 0]
         return tuple(vs)
 
     def sync_weights(self, eval_mode=True):

@@ -1,0 +1,95 @@
+"""Train-mode forward/backward of DeepSpeakerModel on the B200 engine.
+
+Mirrors what autograd does for the reference when the module is in train mode
+(/root/reference/train_triplet.py:203,215-224): BatchNorm uses the batch statistics of each call, running
+statistics are updated in place, and ``loss.backward()`` produces gradients for the 12 conv weights, the 12
+BatchNorm affine pairs and fc (the classifier is outside this path and gets no gradient).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib as L
+from .engine import conv_bn_modules
+
+
+def _train_params(module):
+    """The 38 parameters the path differentiates, in a fixed order: 12 x (conv.weight, bn.weight, bn.bias), fc.weight, fc.bias."""
+    ps = []
+    for conv, bn in conv_bn_modules(module):
+        ps += [conv.weight, bn.weight, bn.bias]
+    ps += [module.model.fc.weight, module.model.fc.bias]
+    return ps
+
+
+class _CtxGuard:
+    """Returns the library-side context to the pool if the autograd graph is dropped without a backward."""
+
+    def __init__(self, engine, tctx):
+        self.engine, self.tctx, self.live = engine, tctx, True
+
+    def consume(self):
+        self.live = False
+
+    def __del__(self):
+        try:
+            if self.live and self.engine.handle.value:
+                self.engine.lib.dsk_train_ctx_release(self.engine.handle, self.tctx)
+        except Exception:
+            pass
+
+
+class TrainForwardFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, engine, *params):
+        B, _, T, _ = x.shape
+        emb = torch.empty(B, engine.module_ref.embedding_size, device=x.device, dtype=torch.float32)
+        tctx = ctypes.c_void_p()
+        L.check(engine.lib.dsk_rescnn_forward_train(engine.handle, x.data_ptr(), B, T, emb.data_ptr(), ctypes.byref(tctx),
+                                                    L.cur_stream()), "dsk_rescnn_forward_train")
+        ctx.engine = engine
+        ctx.guard = _CtxGuard(engine, tctx)
+        ctx.save_for_backward(x, *params)  # x must outlive the backward (conv1's weight gradient reads it)
+        return emb
+
+    @staticmethod
+    def backward(ctx, grad_emb):
+        engine = ctx.engine
+        saved = ctx.saved_tensors
+        params = saved[1:]
+        grads = [torch.empty_like(p) for p in params]
+        g = L.DskGrads()
+        for i in range(L.NUM_CONV):
+            g.conv_w[i] = grads[3 * i].data_ptr()
+            g.bn_gamma[i] = grads[3 * i + 1].data_ptr()
+            g.bn_beta[i] = grads[3 * i + 2].data_ptr()
+        g.fc_w = grads[-2].data_ptr()
+        g.fc_b = grads[-1].data_ptr()
+        ge = grad_emb.float().contiguous()
+        with torch.cuda.device(ge.device):
+            L.check(engine.lib.dsk_rescnn_backward(engine.handle, ctx.guard.tctx, ge.data_ptr(), ctypes.byref(g),
+                                                   L.cur_stream()), "dsk_rescnn_backward")
+        ctx.guard.consume()
+        return (None, None) + tuple(grads)
+
+
+def forward_train(engine, x):
+    module = engine.module_ref
+    engine.sync_weights(eval_mode=False)
+    engine.train_calls += 1  # running statistics are about to change: invalidates the eval-mode BN fold
+    params = _train_params(module)
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    if need_grad:
+        emb = TrainForwardFn.apply(x, engine, *params)
+    else:
+        B, _, T, _ = x.shape
+        emb = torch.empty(B, module.embedding_size, device=x.device, dtype=torch.float32)
+        tctx = ctypes.c_void_p()
+        L.check(engine.lib.dsk_rescnn_forward_train(engine.handle, x.data_ptr(), B, T, emb.data_ptr(), ctypes.byref(tctx),
+                                                    L.cur_stream()), "dsk_rescnn_forward_train")
+        L.check(engine.lib.dsk_train_ctx_release(engine.handle, tctx), "dsk_train_ctx_release")
+    # nn.BatchNorm2d bookkeeping in train mode
+    torch._foreach_add_([bn.num_batches_tracked for _, bn in conv_bn_modules(module)], 1)
+    return emb

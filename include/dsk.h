@@ -66,6 +66,7 @@ typedef struct {
 } dsk_grads;
 
 typedef struct dsk_handle_s* dsk_handle;
+typedef struct dsk_train_ctx_s* dsk_train_ctx; /* what one train-mode forward saved for its backward */
 
 const char* dsk_last_error(void);
 int32_t dsk_version(void);
@@ -84,6 +85,22 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream);
  * T must be a multiple of 16. */
 int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, int32_t mode,
                            void* stream);
+
+/* DeepSpeakerModel.forward with the module in train mode (train_triplet.py:203,215): BatchNorm uses the batch
+ * statistics of THIS call (the reference forwards a, p and n separately, so statistics are per call) and updates
+ * running_mean / running_var in place (momentum 0.1, unbiased variance).  Saves activations in *ctx for
+ * dsk_rescnn_backward; x must stay alive until then.  Contexts are pooled inside the handle. */
+int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, dsk_train_ctx* ctx,
+                                 void* stream);
+/* Backward of that forward (what loss.backward() triggers, train_triplet.py:223): grad_emb (B,E) fp32 ->
+ * gradients of every conv / BN / fc parameter, written (not accumulated) into `grads`.  Consumes the context. */
+int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx ctx, const float* grad_emb, const dsk_grads* grads,
+                            void* stream);
+/* Return an unused context to the pool (forward without backward, e.g. under no_grad). */
+int32_t dsk_train_ctx_release(dsk_handle h, dsk_train_ctx ctx);
+/* fp16 operands: gradients of activations are multiplied by this power of two inside the backward and divided
+ * out of every parameter gradient (0 = automatic: 2^(9+floor(log2 B)) capped at 2^16 for fp16, 1 for bf16). */
+int32_t dsk_set_loss_scale(dsk_handle h, float scale);
 
 /* Per-launch device timing of the next dsk_rescnn_forward calls: when enabled, CUDA events are recorded on
  * `stream` around every kernel of the forward (order: conv1, the 11 tensor-core convs in network order,
