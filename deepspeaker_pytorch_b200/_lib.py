@@ -91,12 +91,19 @@ SIGNATURES = {
     "dsk_rescnn_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "dsk_rescnn_forward_train": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_void_p), c_void_p]),
     "dsk_rescnn_backward": (c_int32, [c_void_p, c_void_p, c_void_p, POINTER(DskGrads), c_void_p]),
+    "dsk_train_ctx_read": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "dsk_train_ctx_release": (c_int32, [c_void_p, c_void_p]),
     "dsk_set_loss_scale": (c_int32, [c_void_p, c_float]),
     "dsk_set_profiling": (c_int32, [c_void_p, c_int32]),
     "dsk_get_launch_times": (c_int32, [c_void_p, c_void_p, c_int32, POINTER(c_int32)]),
     "dsk_conv2d_nhwc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                   c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "dsk_conv2d_dgrad_nhwc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                        c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "dsk_conv2d_wgrad_nhwc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                        c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "dsk_bn_act_train_forward": (c_int32, [c_void_p] * 10 + [c_int64, c_int32, c_void_p]),
+    "dsk_bn_act_train_backward": (c_int32, [c_void_p] * 11 + [c_int64, c_int32, c_float, c_void_p]),
     "dsk_pack_conv_weight": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "dsk_nchw_f32_to_nhwc16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "dsk_nhwc16_to_nchw_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),

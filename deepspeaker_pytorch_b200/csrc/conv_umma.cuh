@@ -61,7 +61,9 @@ struct ConvSmem {
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kScaleBiasBytes + kBarBytes + 1024;
 };
 
-template <int N_TILE, bool BF16>
+// OUT_F32: the epilogue stores fp32 (no residual / clip): used for the pre-BatchNorm conv output of the
+// train-mode forward, which must not be rounded to 16 bit before the batch statistics are applied.
+template <int N_TILE, bool BF16, bool OUT_F32 = false>
 __global__ void __launch_bounds__(256, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -213,6 +215,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       decode(tile, c0, w0, h0, n0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if constexpr (OUT_F32) {
+#pragma unroll 1
+        for (int j = 0; j < N_TILE / 32; ++j) {  // 32 fp32 channels = one 128-byte staging row
+          uint8_t* stg = smem_stg + buf * kATileBytes;
+          if (etid == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          uint32_t v0[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 32, v0);
+          tmem_ld_wait();
+          const float* sc = smem_scale + c0 + j * 32;
+          const float* bi = smem_bias + c0 + j * 32;
+          uint8_t* my_row = stg + row * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint4 o;
+            o.x = __float_as_uint(fmaf(__uint_as_float(v0[q * 4 + 0]), sc[q * 4 + 0], bi[q * 4 + 0]));
+            o.y = __float_as_uint(fmaf(__uint_as_float(v0[q * 4 + 1]), sc[q * 4 + 1], bi[q * 4 + 1]));
+            o.z = __float_as_uint(fmaf(__uint_as_float(v0[q * 4 + 2]), sc[q * 4 + 2], bi[q * 4 + 2]));
+            o.w = __float_as_uint(fmaf(__uint_as_float(v0[q * 4 + 3]), sc[q * 4 + 3], bi[q * 4 + 3]));
+            *reinterpret_cast<uint4*>(my_row + ((q ^ (row & 7)) << 4)) = o;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (etid == 0) {
+            tma_store_5d(&tmOut, stg, p.out_c_base + c0 + j * 32, w0, p.out_ph, h0, n0);
+            tma_store_commit();
+          }
+          buf ^= 1;
+        }
+      } else {
 #pragma unroll 1
       for (int j = 0; j < kChunks; ++j) {
         uint8_t* stg = smem_stg + buf * kATileBytes;
@@ -273,6 +305,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_store_commit();
         }
         buf ^= 1;
+      }
       }
       // accumulator fully read: hand the TMEM buffer back to the MMA warp
       tc_fence_before();

@@ -65,7 +65,7 @@ EncodeTiledFn get_encode_fn() {
 // 16-bit tensor map, 128B swizzle, zero OOB fill. dims/strides innermost first; strides[i] is the byte
 // stride of dim i+1.
 int make_tmap(CUtensorMap* out, bool bf16, const void* ptr, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box) {
+              const uint64_t* strides_bytes, const uint32_t* box, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(DSK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gd[5];
@@ -78,7 +78,8 @@ int make_tmap(CUtensorMap* out, bool bf16, const void* ptr, int rank, const uint
     es[i] = 1;
     if (i < rank - 1) gs[i] = strides_bytes[i];
   }
-  CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+  CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : (bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), rank,
                   const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -95,6 +96,7 @@ struct ConvLaunch {
   dsk::ConvParams p;
   int n_tile = 0;
   int grid = 0;
+  bool out_f32 = false;
 };
 
 struct WgradLaunch {
@@ -163,18 +165,14 @@ struct dsk_train_ctx_s {
   bool forward_done = false;
   const float* x = nullptr;            // borrowed: the caller keeps the input alive until backward
   uint8_t* base = nullptr;             // one allocation
-  void* raw[DSK_NUM_CONV] = {};        // conv outputs before BN (16-bit NHWC)
+  float* raw[DSK_NUM_CONV] = {};       // conv outputs before BN (fp32 NHWC: BN must see unrounded values)
   void* y[DSK_NUM_CONV] = {};          // after BN (+res) + clip (16-bit NHWC)
-  void* yT[DSK_NUM_CONV] = {};         // channel-major copy of y[i], i < 11 (operand of conv i+1's weight gradient)
-  dsk::TransposeGeom tgY[DSK_NUM_CONV];
-  dsk::TransposeGeom tgG[DSK_NUM_CONV];
   float* mean[DSK_NUM_CONV] = {};
   float* rstd[DSK_NUM_CONV] = {};
   float *pooled = nullptr, *fc_out = nullptr, *inv_norm = nullptr;
   float *scale_t = nullptr, *shift_t = nullptr, *partial = nullptr, *coef = nullptr;
   float *g_fc = nullptr, *dP = nullptr, *dwacc = nullptr, *c1part = nullptr;
-  void *gA = nullptr, *gB = nullptr, *G = nullptr, *GT = nullptr, *gres = nullptr;
-  size_t gt_bytes = 0;
+  void *gA = nullptr, *gB = nullptr, *G = nullptr, *gres = nullptr;
   ConvLaunch conv[DSK_NUM_CONV];       // forward convs 1..11 (raw output, no epilogue math)
   ConvLaunch dgrad[DSK_NUM_CONV][4];
   int n_dgrad[DSK_NUM_CONV] = {};
@@ -203,9 +201,9 @@ void choose_tile(int B, int Hout, int Wout, int total, int& wt, int& hb, int& nb
   }
 }
 
-template <int N_TILE, bool BF16>
+template <int N_TILE, bool BF16, bool OUT_F32 = false>
 int launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
-  auto kern = dsk::conv_umma_kernel<N_TILE, BF16>;
+  auto kern = dsk::conv_umma_kernel<N_TILE, BF16, OUT_F32>;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dsk::ConvSmem<N_TILE>::kTotal));
@@ -217,6 +215,22 @@ int launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
 }
 
 int launch_conv(const dsk_handle_s* h, const ConvLaunch& L, cudaStream_t s) {
+  if (L.out_f32) {
+    if (h->bf16) {
+      switch (L.n_tile) {
+        case 64: return launch_conv_t<64, true, true>(L, s);
+        case 128: return launch_conv_t<128, true, true>(L, s);
+        case 256: return launch_conv_t<256, true, true>(L, s);
+      }
+    } else {
+      switch (L.n_tile) {
+        case 64: return launch_conv_t<64, false, true>(L, s);
+        case 128: return launch_conv_t<128, false, true>(L, s);
+        case 256: return launch_conv_t<256, false, true>(L, s);
+      }
+    }
+    return fail(DSK_ERR_INVALID, "unsupported N tile %d", L.n_tile);
+  }
   if (h->bf16) {
     switch (L.n_tile) {
       case 64: return launch_conv_t<64, true>(L, s);
@@ -271,7 +285,10 @@ struct TapTable {
 // Generic builder: out[pixel grid Hgrid x Wgrid x B][n_out] = epilogue( sum_taps A(tap-shifted)[.., k] * Wt[tap][n_out][k] ).
 int build_conv_core(const dsk_handle_s* h, ConvLaunch* L, const View5& a, const void* wpk, int k_ch, int n_out,
                     int w_slices, const View5& o, const void* res, int B, int Hgrid, int Wgrid, const TapTable& taps,
-                    int flags, float clip_hi, const float* scale, const float* bias, int out_c_base, int out_ph) {
+                    int flags, float clip_hi, const float* scale, const float* bias, int out_c_base, int out_ph,
+                    bool out_f32 = false) {
+  if (out_f32 && (flags != 0)) return fail(DSK_ERR_INVALID, "conv: fp32 output supports neither residual nor clip");
+  L->out_f32 = out_f32;
   if (k_ch % 64 || n_out % 64 || k_ch < 64 || n_out < 64 || n_out > 512)
     return fail(DSK_ERR_INVALID, "conv: channel counts must be multiples of 64 and <= 512 outputs (got %d, %d)", k_ch, n_out);
   if (Wgrid > 128 || 128 % Wgrid) return fail(DSK_ERR_INVALID, "conv: output width %d must divide 128", Wgrid);
@@ -318,6 +335,13 @@ int build_conv_core(const dsk_handle_s* h, ConvLaunch* L, const View5& a, const 
   uint32_t wb[3] = {64, (uint32_t)n_tile, 1};
   rc = make_tmap(&L->tmB, bf, wpk, 3, wd, ws, wb);
   if (rc) return rc;
+  if (out_f32) {
+    uint64_t str4[4] = {o.str[0] * 2, o.str[1] * 2, o.str[2] * 2, o.str[3] * 2};  // the view was built for 2-byte elements
+    uint32_t boxO[5] = {32, (uint32_t)p.wt, 1, (uint32_t)p.hb, (uint32_t)p.nb};
+    rc = make_tmap(&L->tmOut, bf, o.ptr, 5, o.dims, str4, boxO, true);
+    if (rc) return rc;
+    return make_tmap(&L->tmRes, bf, o.ptr, 5, o.dims, str4, boxO, true);
+  }
   rc = make_tmap(&L->tmOut, bf, o.ptr, 5, o.dims, o.str, boxA);
   if (rc) return rc;
   return make_tmap(&L->tmRes, bf, (flags & dsk::CONV_RESIDUAL) ? res : o.ptr, 5, o.dims, o.str, boxA);
@@ -326,7 +350,7 @@ int build_conv_core(const dsk_handle_s* h, ConvLaunch* L, const View5& a, const 
 // Forward conv layer on NHWC 16-bit tensors (3x3 s1 p1 or 5x5 s2 p2).
 int build_conv(const dsk_handle_s* h, ConvLaunch* L, const void* in, const void* wpk, const float* scale,
                const float* bias, const void* res, void* out, int B, int Hin, int Win, int cin, int cout, int ksize,
-               int stride, int flags, float clip_hi) {
+               int stride, int flags, float clip_hi, bool out_f32 = false) {
   if (!((ksize == 3 && stride == 1) || (ksize == 5 && stride == 2)))
     return fail(DSK_ERR_INVALID, "conv: only 3x3 s1 p1 and 5x5 s2 p2 are supported (got k=%d s=%d)", ksize, stride);
   if (stride == 2 && ((Hin & 1) || (Win & 1)))
@@ -344,7 +368,7 @@ int build_conv(const dsk_handle_s* h, ConvLaunch* L, const void* in, const void*
   const View5 a = stride == 1 ? nhwc_view(in, B, Hin, Win, cin) : nhwc_parity_view(in, B, Hin, Win, cin);
   const View5 o = nhwc_view(out, B, Hout, Wout, cout);
   return build_conv_core(h, L, a, wpk, cin, cout, ksize * ksize, o, res, B, Hout, Wout, tt, flags, clip_hi, scale, bias,
-                         0, 0);
+                         0, 0, out_f32);
 }
 
 // Data gradient of a 3x3 s1 p1 conv: g_in = conv(G, rot180(W)^T) (+ res).  G (B,H,W,cout) -> g_in (B,H,W,cin).
@@ -371,64 +395,59 @@ int build_dgrad_s2(const dsk_handle_s* h, ConvLaunch* L, const void* G, const vo
 }
 
 // ---- weight gradient --------------------------------------------------------------------------------------------
-// channel-major 16-bit tensor [c][n][plane][Hp][Wp] as the TMA view (w, h, plane, n, c)
-View5 cmajor_view(const void* ptr, int N, int planes, int Hp, int Wp, int C) {
-  View5 v;
-  v.ptr = ptr;
-  v.dims[0] = Wp; v.dims[1] = Hp; v.dims[2] = planes; v.dims[3] = N; v.dims[4] = C;
-  v.str[0] = 2ull * Wp; v.str[1] = 2ull * Hp * Wp; v.str[2] = 2ull * planes * Hp * Wp;
-  v.str[3] = 2ull * N * planes * Hp * Wp;
-  return v;
-}
-
-// dW[tap][cout][cin] += GT (x) XT over the pixel grid (Hg x Wg(p) x N).  ksize/stride as the forward conv.
-int build_wgrad(const dsk_handle_s* h, WgradLaunch* L, const void* GT, const void* XT, int N, int Hg, int Wgp,
-                int x_planes, int cout, int cin, int ksize, int stride, float* dwacc) {
+// dW[tap][cout][cin] += G (x) X over the output pixel grid (B x Hout x Wout).  G: NHWC gradient w.r.t. the raw conv
+// output; X: the conv's NHWC input (B, Hin, Win, cin).  ksize/stride as the forward conv.
+int build_wgrad(const dsk_handle_s* h, WgradLaunch* L, const void* G, const void* X, int B, int Hin, int Win, int cout,
+                int cin, int ksize, int stride, float* dwacc) {
   const bool bf = h->bf16;
   dsk::WgradParams& p = L->p;
   memset(&p, 0, sizeof(p));
-  if (Wgp < 8 || Wgp > 64 || 64 % Wgp) return fail(DSK_ERR_INVALID, "wgrad: row pitch %d unsupported", Wgp);
-  choose_tile(N, Hg, Wgp, 64, p.kw, p.kh, p.kn);
-  p.chunks_w = (Wgp + p.kw - 1) / p.kw;
-  p.chunks_h = (Hg + p.kh - 1) / p.kh;
-  p.chunks_n = (N + p.kn - 1) / p.kn;
+  const int Hout = Hin / stride, Wout = Win / stride;
+  if (Wout > 128 || 128 % Wout) return fail(DSK_ERR_INVALID, "wgrad: output width %d must divide 128", Wout);
+  choose_tile(B, Hout, Wout, 128, p.wt, p.hb, p.nb);
+  p.chunks_w = (Wout + p.wt - 1) / p.wt;
+  p.chunks_h = (Hout + p.hb - 1) / p.hb;
+  p.chunks_n = (B + p.nb - 1) / p.nb;
   p.taps = ksize * ksize;
   p.cout = cout;
   p.cin = cin;
-  p.co_tiles = (cout + 127) / 128;
-  const int n_tile = cin >= 256 ? 256 : (cin >= 128 ? 128 : 64);
+  p.swapped = cout == 64 ? 1 : 0;
+  if (p.swapped && cin != 64) return fail(DSK_ERR_INVALID, "wgrad: cout == 64 requires cin == 64");
+  const int n_tile = p.swapped ? 64 : (cin >= 128 ? 128 : 64);
   L->n_tile = n_tile;
-  p.ci_tiles = (cin + n_tile - 1) / n_tile;
+  p.co_tiles = p.swapped ? 1 : cout / 128;
+  p.ci_tiles = p.swapped ? 1 : cin / n_tile;
   p.dw = dwacc;
   for (int r = 0; r < ksize; ++r)
     for (int s = 0; s < ksize; ++s) {
       const int t = r * ksize + s;
       if (stride == 1) {
+        p.tap_c[t] = 0;
         p.tap_dw[t] = (int8_t)(s - 1);
+        p.tap_ph[t] = 0;
         p.tap_dh[t] = (int8_t)(r - 1);
-        p.tap_plane[t] = 0;
       } else {
+        p.tap_c[t] = (int16_t)((s & 1) * cin);
         p.tap_dw[t] = (int8_t)((s - 2) >> 1);
+        p.tap_ph[t] = (int8_t)(r & 1);
         p.tap_dh[t] = (int8_t)((r - 2) >> 1);
-        p.tap_plane[t] = (int8_t)((r & 1) * 2 + (s & 1));
       }
     }
   const int total_chunks = p.chunks_w * p.chunks_h * p.chunks_n;
-  const int items0 = p.taps * p.co_tiles * p.ci_tiles;
+  const int items0 = (p.swapped ? (p.taps + 1) / 2 : p.taps) * p.co_tiles * p.ci_tiles;
   int ksplit = (2 * h->num_sms + items0 - 1) / items0;
-  const int max_split = total_chunks / 8 > 0 ? total_chunks / 8 : 1;
+  const int max_split = total_chunks / 4 > 0 ? total_chunks / 4 : 1;
   if (ksplit > max_split) ksplit = max_split;
   if (ksplit < 1) ksplit = 1;
   p.ksplit = ksplit;
   const int items = items0 * ksplit;
   L->grid = items < h->num_sms ? items : h->num_sms;
-  const View5 g = cmajor_view(GT, N, 1, Hg, Wgp, cout);
-  const View5 x = cmajor_view(XT, N, x_planes, Hg, Wgp, cin);
-  uint32_t boxG[5] = {(uint32_t)p.kw, (uint32_t)p.kh, 1, (uint32_t)p.kn, 128};
-  uint32_t boxX[5] = {(uint32_t)p.kw, (uint32_t)p.kh, 1, (uint32_t)p.kn, (uint32_t)n_tile};
-  int rc = make_tmap(&L->tmG, bf, g.ptr, 5, g.dims, g.str, boxG);
+  const View5 g = nhwc_view(G, B, Hout, Wout, cout);
+  const View5 x = stride == 1 ? nhwc_view(X, B, Hin, Win, cin) : nhwc_parity_view(X, B, Hin, Win, cin);
+  uint32_t box[5] = {64, (uint32_t)p.wt, 1, (uint32_t)p.hb, (uint32_t)p.nb};
+  int rc = make_tmap(&L->tmG, bf, g.ptr, 5, g.dims, g.str, box);
   if (rc) return rc;
-  return make_tmap(&L->tmX, bf, x.ptr, 5, x.dims, x.str, boxX);
+  return make_tmap(&L->tmX, bf, x.ptr, 5, x.dims, x.str, box);
 }
 
 template <int N_TILE, bool BF16>
@@ -449,13 +468,11 @@ int launch_wgrad(const dsk_handle_s* h, const WgradLaunch& L, cudaStream_t s) {
     switch (L.n_tile) {
       case 64: return launch_wgrad_t<64, true>(L, s);
       case 128: return launch_wgrad_t<128, true>(L, s);
-      case 256: return launch_wgrad_t<256, true>(L, s);
     }
   } else {
     switch (L.n_tile) {
       case 64: return launch_wgrad_t<64, false>(L, s);
       case 128: return launch_wgrad_t<128, false>(L, s);
-      case 256: return launch_wgrad_t<256, false>(L, s);
     }
   }
   return fail(DSK_ERR_INVALID, "unsupported wgrad N tile %d", L.n_tile);
@@ -743,19 +760,6 @@ int32_t dsk_get_launch_times(dsk_handle h, float* ms_out, int32_t cap, int32_t* 
 
 
 // ---- training ---------------------------------------------------------------------------------------------------
-static dsk::TransposeGeom make_geom(int N, int H, int W, int planes) {
-  dsk::TransposeGeom g;
-  g.H = H;
-  g.W = W;
-  g.planes = planes;
-  g.Hp = planes == 1 ? H : H / 2;
-  const int w = planes == 1 ? W : W / 2;
-  g.Wp = w < 8 ? 8 : w;
-  g.cstride = static_cast<long>(N) * planes * g.Hp * g.Wp;
-  g.dense = (planes == 1 && g.Wp == W) ? 1 : 0;
-  return g;
-}
-
 static int stat_blocks(long M, int C) {
   long gx = kStatBlocksMax / (C / 64);
   const long need = (M + 31) / 32;
@@ -773,23 +777,15 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
     bytes += (n + 1023) / 1024 * 1024;
     return o;
   };
-  size_t o_raw[DSK_NUM_CONV], o_y[DSK_NUM_CONV], o_yT[DSK_NUM_CONV], o_mean[DSK_NUM_CONV], o_rstd[DSK_NUM_CONV];
-  size_t max_act = 0, max_gt = 0;
+  size_t o_raw[DSK_NUM_CONV], o_y[DSK_NUM_CONV], o_mean[DSK_NUM_CONV], o_rstd[DSK_NUM_CONV];
+  size_t max_act = 0;
   for (int i = 0; i < DSK_NUM_CONV; ++i) {
     int H, W, C;
     act_shape(i, T, H, W, C);
     const size_t act = static_cast<size_t>(B) * H * W * C * 2;
     if (act > max_act) max_act = act;
-    o_raw[i] = take(act);
+    o_raw[i] = take(2 * act);
     o_y[i] = take(act);
-    c->tgG[i] = make_geom(B, H, W, 1);
-    const size_t gt = static_cast<size_t>(c->tgG[i].cstride) * C * 2;
-    if (gt > max_gt) max_gt = gt;
-    if (i < DSK_NUM_CONV - 1) {
-      const bool next_s2 = ((i + 1) % 3) == 0;
-      c->tgY[i] = make_geom(B, H, W, next_s2 ? 4 : 1);
-      o_yT[i] = take(static_cast<size_t>(c->tgY[i].cstride) * C * 2);
-    }
     o_mean[i] = take(C * 4);
     o_rstd[i] = take(C * 4);
   }
@@ -798,14 +794,13 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
   const size_t o_part = take(static_cast<size_t>(kStatBlocksMax) * 2 * 512 * 4), o_coef = take(3 * 512 * 4);
   const size_t o_gfc = take(static_cast<size_t>(B) * h->emb * 4), o_dP = take(static_cast<size_t>(B) * 2048 * 4);
   const size_t o_dw = take(static_cast<size_t>(25) * 512 * 256 * 4), o_c1 = take(static_cast<size_t>(1184) * 1600 * 4);
-  const size_t o_gA = take(max_act), o_gB = take(max_act), o_G = take(max_act), o_GT = take(max_gt), o_gres = take(max_act);
+  const size_t o_gA = take(max_act), o_gB = take(max_act), o_G = take(max_act), o_gres = take(max_act);
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->base), bytes));
-  CUDA_TRY(cudaMemset(c->base, 0, bytes));  // pad columns of the channel-major copies must stay zero
+  CUDA_TRY(cudaMemset(c->base, 0, bytes));
   uint8_t* b = c->base;
   for (int i = 0; i < DSK_NUM_CONV; ++i) {
-    c->raw[i] = b + o_raw[i];
+    c->raw[i] = reinterpret_cast<float*>(b + o_raw[i]);
     c->y[i] = b + o_y[i];
-    c->yT[i] = i < DSK_NUM_CONV - 1 ? b + o_yT[i] : nullptr;
     c->mean[i] = reinterpret_cast<float*>(b + o_mean[i]);
     c->rstd[i] = reinterpret_cast<float*>(b + o_rstd[i]);
   }
@@ -823,8 +818,6 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
   c->gA = b + o_gA;
   c->gB = b + o_gB;
   c->G = b + o_G;
-  c->GT = b + o_GT;
-  c->gt_bytes = max_gt;
   c->gres = b + o_gres;
   // launch descriptors
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
@@ -833,7 +826,7 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
     act_shape(i - 1, T, Hi, Wi, Ci);
     act_shape(i, T, Ho, Wo, Co);
     int rc = build_conv(h, &c->conv[i], c->y[i - 1], h->wpk[i], nullptr, nullptr, nullptr, c->raw[i], B, Hi, Wi, lc.cin,
-                        lc.cout, lc.ksize, lc.stride, 0, 0.f);
+                        lc.cout, lc.ksize, lc.stride, 0, 0.f, true);
     if (rc) return rc;
     // gradient w.r.t. y[i-1] lands in the buffer that is not holding the gradient w.r.t. y[i]
     void* g_out = ((DSK_NUM_CONV - 1 - i) % 2 == 0) ? c->gB : c->gA;
@@ -847,8 +840,7 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
       c->n_dgrad[i] = 4;
     }
     if (rc) return rc;
-    rc = build_wgrad(h, &c->wgrad[i], c->GT, c->yT[i - 1], B, Ho, c->tgG[i].Wp, c->tgY[i - 1].planes, lc.cout, lc.cin,
-                     lc.ksize, lc.stride, c->dwacc);
+    rc = build_wgrad(h, &c->wgrad[i], c->G, c->y[i - 1], B, Hi, Wi, lc.cout, lc.cin, lc.ksize, lc.stride, c->dwacc);
     if (rc) return rc;
   }
   *out = c;
@@ -902,8 +894,7 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
     const long M = static_cast<long>(B) * H * W;
     if (i == 0) {
       const int blocks = B * ((T / 2 + 7) / 8);
-      if (bf) dsk::conv1_kernel<true><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->ones, h->zeros, (uint16_t*)c->raw[0], T, 0, 0.f);
-      else dsk::conv1_kernel<false><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->ones, h->zeros, (uint16_t*)c->raw[0], T, 0, 0.f);
+      dsk::conv1_kernel<false, true><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->ones, h->zeros, c->raw[0], T, 0, 0.f);
       KERNEL_CHECK();
     } else {
       rc = launch_conv(h, c->conv[i], s);
@@ -911,8 +902,7 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
     }
     const int gx = stat_blocks(M, C);
     dim3 gs(gx, C / 64);
-    if (bf) dsk::bn_stats_partial_kernel<true><<<gs, 256, 0, s>>>((const uint16_t*)c->raw[i], M, C, c->partial);
-    else dsk::bn_stats_partial_kernel<false><<<gs, 256, 0, s>>>((const uint16_t*)c->raw[i], M, C, c->partial);
+    dsk::bn_stats_partial_kernel<<<gs, 256, 0, s>>>(c->raw[i], M, C, c->partial);
     KERNEL_CHECK();
     dsk::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], h->w.bn_beta[i],
                                                            h->w.bn_running_mean[i], h->w.bn_running_var[i], 0.1f, 1e-5f,
@@ -921,11 +911,11 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
     const uint16_t* res = (i % 3 == 2) ? (const uint16_t*)c->y[i - 2] : nullptr;
     dim3 ga(static_cast<unsigned>((M + 63) / 64), C / 64);
     if (bf)
-      dsk::bn_apply_kernel<true><<<ga, 256, 0, s>>>((const uint16_t*)c->raw[i], c->scale_t, c->shift_t, res, (uint16_t*)c->y[i],
-                                                    (uint16_t*)c->yT[i], M, C, 20.0f, c->tgY[i]);
+      dsk::bn_apply_kernel<true><<<ga, 256, 0, s>>>(c->raw[i], c->scale_t, c->shift_t, res, (uint16_t*)c->y[i],
+                                                    M, C, 20.0f);
     else
-      dsk::bn_apply_kernel<false><<<ga, 256, 0, s>>>((const uint16_t*)c->raw[i], c->scale_t, c->shift_t, res, (uint16_t*)c->y[i],
-                                                     (uint16_t*)c->yT[i], M, C, 20.0f, c->tgY[i]);
+      dsk::bn_apply_kernel<false><<<ga, 256, 0, s>>>(c->raw[i], c->scale_t, c->shift_t, res, (uint16_t*)c->y[i],
+                                                     M, C, 20.0f);
     KERNEL_CHECK();
   }
   {
@@ -969,7 +959,6 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
     else dsk::pool_bwd_kernel<false><<<B, 256, 0, s>>>(c->dP, (uint16_t*)c->gA, H4, 2048, S / H4);
     KERNEL_CHECK();
   }
-  CUDA_TRY(cudaMemsetAsync(c->GT, 0, c->gt_bytes, s));  // zero pad columns for the padded stage-4 geometry
   for (int i = DSK_NUM_CONV - 1; i >= 0; --i) {
     int H, W, C;
     act_shape(i, T, H, W, C);
@@ -978,10 +967,10 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
     const int gx = stat_blocks(M, C);
     dim3 gs(gx, C / 64);
     if (bf)
-      dsk::bn_bwd_reduce_kernel<true><<<gs, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], (const uint16_t*)c->raw[i], c->mean[i],
+      dsk::bn_bwd_reduce_kernel<true><<<gs, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], c->raw[i], c->mean[i],
                                                          c->rstd[i], M, C, 20.0f, c->partial);
     else
-      dsk::bn_bwd_reduce_kernel<false><<<gs, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], (const uint16_t*)c->raw[i], c->mean[i],
+      dsk::bn_bwd_reduce_kernel<false><<<gs, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], c->raw[i], c->mean[i],
                                                           c->rstd[i], M, C, 20.0f, c->partial);
     KERNEL_CHECK();
     dsk::bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], c->rstd[i], invS,
@@ -990,13 +979,11 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
     uint16_t* gres = (i % 3 == 2) ? (uint16_t*)c->gres : nullptr;
     dim3 ga(static_cast<unsigned>((M + 63) / 64), C / 64);
     if (bf)
-      dsk::bn_bwd_apply_kernel<true><<<ga, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], (const uint16_t*)c->raw[i], c->mean[i],
-                                                        c->rstd[i], c->coef, (uint16_t*)c->G, (uint16_t*)c->GT, gres, M, C,
-                                                        20.0f, c->tgG[i]);
+      dsk::bn_bwd_apply_kernel<true><<<ga, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], c->raw[i], c->mean[i],
+                                                        c->rstd[i], c->coef, (uint16_t*)c->G, gres, M, C, 20.0f);
     else
-      dsk::bn_bwd_apply_kernel<false><<<ga, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], (const uint16_t*)c->raw[i], c->mean[i],
-                                                         c->rstd[i], c->coef, (uint16_t*)c->G, (uint16_t*)c->GT, gres, M, C,
-                                                         20.0f, c->tgG[i]);
+      dsk::bn_bwd_apply_kernel<false><<<ga, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], c->raw[i], c->mean[i],
+                                                         c->rstd[i], c->coef, (uint16_t*)c->G, gres, M, C, 20.0f);
     KERNEL_CHECK();
     const LayerCfg lc = layer_cfg(i);
     if (i == 0) {
@@ -1026,10 +1013,151 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
   return DSK_OK;
 }
 
+int32_t dsk_train_ctx_read(dsk_handle h, dsk_train_ctx c, int32_t which, int32_t layer, float* out_nchw, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!c || !c->forward_done) return fail(DSK_ERR_STATE, "dsk_train_ctx_read: context has no pending forward");
+  if (layer < 0 || layer >= DSK_NUM_CONV || !out_nchw || which < 0 || which > 1)
+    return fail(DSK_ERR_INVALID, "dsk_train_ctx_read: bad arguments");
+  int H, W, C;
+  act_shape(layer, c->T, H, W, C);
+  const long n = static_cast<long>(c->B) * C * H * W;
+  const int blocks = static_cast<int>((n + 255) / 256 < 65535 ? (n + 255) / 256 : 65535);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (which == 0)
+    dsk::nhwc_f32_to_nchw_kernel<<<blocks, 256, 0, s>>>(c->raw[layer], out_nchw, c->B, C, H * W);
+  else if (h->bf16)
+    dsk::nhwc16_to_nchw_kernel<true><<<blocks, 256, 0, s>>>((const uint16_t*)c->y[layer], out_nchw, c->B, C, H * W);
+  else
+    dsk::nhwc16_to_nchw_kernel<false><<<blocks, 256, 0, s>>>((const uint16_t*)c->y[layer], out_nchw, c->B, C, H * W);
+  KERNEL_CHECK();
+  return DSK_OK;
+}
+
 int32_t dsk_train_ctx_release(dsk_handle h, dsk_train_ctx c) {
   if (!h || !c) return fail(DSK_ERR_INVALID, "dsk_train_ctx_release: null argument");
   c->in_use = false;
   c->forward_done = false;
+  return DSK_OK;
+}
+
+
+// ---- per-op entry points for unit tests of the backward building blocks -------------------------------------------
+int32_t dsk_conv2d_dgrad_nhwc(dsk_handle h, const void* G, const float* w_oihw, const void* res, void* gin, int32_t B,
+                              int32_t Hin, int32_t Win, int32_t cin, int32_t cout, int32_t ksize, int32_t stride,
+                              void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!G || !w_oihw || !gin) return fail(DSK_ERR_INVALID, "dsk_conv2d_dgrad_nhwc: null pointer");
+  if (!((ksize == 3 && stride == 1) || (ksize == 5 && stride == 2)))
+    return fail(DSK_ERR_INVALID, "dgrad: only 3x3 s1 p1 and 5x5 s2 p2 are supported");
+  if (stride == 2 && res) return fail(DSK_ERR_INVALID, "dgrad: residual only with stride 1");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int taps = ksize * ksize;
+  const long n = static_cast<long>(cout) * cin * taps;
+  void* wpk = nullptr;
+  CUDA_TRY(cudaMallocAsync(&wpk, n * 2, s));
+  const int blocks = static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  if (h->bf16) dsk::pack_conv_weight_dgrad_kernel<true><<<blocks, 256, 0, s>>>(w_oihw, (uint16_t*)wpk, cout, cin, taps, stride == 1);
+  else dsk::pack_conv_weight_dgrad_kernel<false><<<blocks, 256, 0, s>>>(w_oihw, (uint16_t*)wpk, cout, cin, taps, stride == 1);
+  KERNEL_CHECK();
+  const int Hout = Hin / stride, Wout = Win / stride;
+  ConvLaunch L;
+  if (stride == 1) {
+    rc = build_dgrad_s1(h, &L, G, wpk, res, gin, B, Hin, Win, cin, cout);
+    if (!rc) rc = launch_conv(h, L, s);
+  } else {
+    for (int cls = 0; cls < 4 && !rc; ++cls) {
+      rc = build_dgrad_s2(h, &L, G, wpk, gin, B, Hout, Wout, cin, cout, cls >> 1, cls & 1);
+      if (!rc) rc = launch_conv(h, L, s);
+    }
+  }
+  CUDA_TRY(cudaFreeAsync(wpk, s));
+  return rc;
+}
+
+int32_t dsk_conv2d_wgrad_nhwc(dsk_handle h, const void* G, const void* X, float* dw_oihw, int32_t B, int32_t Hin,
+                              int32_t Win, int32_t cin, int32_t cout, int32_t ksize, int32_t stride, float mult,
+                              void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!G || !X || !dw_oihw) return fail(DSK_ERR_INVALID, "dsk_conv2d_wgrad_nhwc: null pointer");
+  if (!((ksize == 3 && stride == 1) || (ksize == 5 && stride == 2)))
+    return fail(DSK_ERR_INVALID, "wgrad: only 3x3 s1 p1 and 5x5 s2 p2 are supported");
+  if (cin % 64 || cout % 64) return fail(DSK_ERR_INVALID, "wgrad: channel counts must be multiples of 64");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int taps = ksize * ksize;
+  const size_t n = static_cast<size_t>(taps) * cout * cin;
+  float* acc = nullptr;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&acc), n * 4, s));
+  CUDA_TRY(cudaMemsetAsync(acc, 0, n * 4, s));
+  WgradLaunch L;
+  rc = build_wgrad(h, &L, G, X, B, Hin, Win, cout, cin, ksize, stride, acc);
+  if (!rc) rc = launch_wgrad(h, L, s);
+  if (!rc) {
+    dsk::unpack_wgrad_kernel<<<static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, s>>>(
+        acc, dw_oihw, cout, cin, taps, mult);
+    KERNEL_CHECK();
+  }
+  CUDA_TRY(cudaFreeAsync(acc, s));
+  return rc;
+}
+
+// BatchNorm(train) + optional residual + clip on an NHWC tensor viewed as [M][C]: raw fp32 -> y 16-bit, plus the
+// saved mean / rstd (running stats updated in place).
+int32_t dsk_bn_act_train_forward(dsk_handle h, const float* raw, const float* gamma, const float* beta,
+                                 float* running_mean, float* running_var, const void* res, void* y, float* mean,
+                                 float* rstd, int64_t M, int32_t C, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!raw || !gamma || !beta || !running_mean || !running_var || !y || !mean || !rstd || C % 64 || C > 512 || M <= 0)
+    return fail(DSK_ERR_INVALID, "dsk_bn_act_train_forward: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* tmp = nullptr;
+  const int gx = stat_blocks(M, C);
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tmp), (static_cast<size_t>(gx) * 2 * C + 2 * C) * 4, s));
+  float *partial = tmp, *sc = tmp + static_cast<size_t>(gx) * 2 * C, *sh = sc + C;
+  dsk::bn_stats_partial_kernel<<<dim3(gx, C / 64), 256, 0, s>>>(raw, M, C, partial);
+  KERNEL_CHECK();
+  dsk::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, gx, C, M, gamma, beta, running_mean, running_var, 0.1f,
+                                                         1e-5f, mean, rstd, sc, sh);
+  KERNEL_CHECK();
+  dim3 ga(static_cast<unsigned>((M + 63) / 64), C / 64);
+  if (h->bf16) dsk::bn_apply_kernel<true><<<ga, 256, 0, s>>>(raw, sc, sh, (const uint16_t*)res, (uint16_t*)y, M, C, 20.0f);
+  else dsk::bn_apply_kernel<false><<<ga, 256, 0, s>>>(raw, sc, sh, (const uint16_t*)res, (uint16_t*)y, M, C, 20.0f);
+  KERNEL_CHECK();
+  CUDA_TRY(cudaFreeAsync(tmp, s));
+  return DSK_OK;
+}
+
+// Backward of the above: gy (16-bit, w.r.t. y) -> G (16-bit, w.r.t. raw), gres (16-bit, w.r.t. res; may be NULL),
+// dgamma, dbeta (fp32, multiplied by inv_scale).
+int32_t dsk_bn_act_train_backward(dsk_handle h, const void* gy, const void* y, const float* raw, const float* gamma,
+                                  const float* mean, const float* rstd, void* G, void* gres, float* dgamma,
+                                  float* dbeta, int64_t M, int32_t C, float inv_scale, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!gy || !y || !raw || !gamma || !mean || !rstd || !G || !dgamma || !dbeta || C % 64 || C > 512 || M <= 0)
+    return fail(DSK_ERR_INVALID, "dsk_bn_act_train_backward: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* tmp = nullptr;
+  const int gx = stat_blocks(M, C);
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tmp), (static_cast<size_t>(gx) * 2 * C + 3 * C) * 4, s));
+  float *partial = tmp, *coef = tmp + static_cast<size_t>(gx) * 2 * C;
+  dim3 gs(gx, C / 64), ga(static_cast<unsigned>((M + 63) / 64), C / 64);
+  if (h->bf16) {
+    dsk::bn_bwd_reduce_kernel<true><<<gs, 256, 0, s>>>((const uint16_t*)gy, (const uint16_t*)y, raw, mean, rstd, M, C, 20.0f, partial);
+    dsk::bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, gx, C, M, gamma, rstd, inv_scale, dgamma, dbeta, coef);
+    dsk::bn_bwd_apply_kernel<true><<<ga, 256, 0, s>>>((const uint16_t*)gy, (const uint16_t*)y, raw, mean, rstd, coef, (uint16_t*)G,
+                                                      (uint16_t*)gres, M, C, 20.0f);
+  } else {
+    dsk::bn_bwd_reduce_kernel<false><<<gs, 256, 0, s>>>((const uint16_t*)gy, (const uint16_t*)y, raw, mean, rstd, M, C, 20.0f, partial);
+    dsk::bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, gx, C, M, gamma, rstd, inv_scale, dgamma, dbeta, coef);
+    dsk::bn_bwd_apply_kernel<false><<<ga, 256, 0, s>>>((const uint16_t*)gy, (const uint16_t*)y, raw, mean, rstd, coef, (uint16_t*)G,
+                                                       (uint16_t*)gres, M, C, 20.0f);
+  }
+  KERNEL_CHECK();
+  CUDA_TRY(cudaFreeAsync(tmp, s));
   return DSK_OK;
 }
 

@@ -58,10 +58,10 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 // Block = 4 output rows of one utterance; warp = 16 pixels; lane = 2 output channels, whose
 // 50 filter weights live in registers; the input patch is broadcast from shared memory.
 // ---------------------------------------------------------------------------------------------
-template <bool BF16>
+template <bool BF16, bool OUT_F32 = false>
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]*/, const float* __restrict__ scale,
-             const float* __restrict__ bias, uint16_t* __restrict__ out, int T, int do_clip, float clip_hi) {
+             const float* __restrict__ bias, void* __restrict__ out, int T, int do_clip, float clip_hi) {
   constexpr int WIN = 64, WOUT = 32, ROWS = 8, PATCH_ROWS = 2 * ROWS + 3, PATCH_W = WIN + 4;
   __shared__ float patch[PATCH_ROWS][PATCH_W];
   __shared__ float wsm[64 * 25];
@@ -108,7 +108,10 @@ conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]
       a0 = fminf(fmaxf(a0, 0.f), clip_hi);
       a1 = fminf(fmaxf(a1, 0.f), clip_hi);
     }
-    o32[(pix0 + ow) * 32 + lane] = pack2<BF16>(a0, a1);
+    if constexpr (OUT_F32)
+      reinterpret_cast<float2*>(out)[(pix0 + ow) * 32 + lane] = make_float2(a0, a1);
+    else
+      o32[(pix0 + ow) * 32 + lane] = pack2<BF16>(a0, a1);
   }
 }
 

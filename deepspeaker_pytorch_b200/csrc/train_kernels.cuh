@@ -32,6 +32,18 @@ __global__ void nhwc16_to_nchw_kernel(const uint16_t* __restrict__ in, float* __
   }
 }
 
+__global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int HW) {
+  const long total = static_cast<long>(B) * C * HW;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = i % C;
+    const long r = i / C;
+    const int hw = r % HW;
+    const int b = r / HW;
+    out[(static_cast<long>(b) * C + c) * HW + hw] = in[i];
+  }
+}
+
 }  // namespace dsk
 
 // =================================================================================================
@@ -64,31 +76,17 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return o;
 }
 
-// Where pixel m = (n, h, w) of a [N][H][W] grid lands in the channel-major ("transposed") copy used by the
-// weight-gradient GEMM: [c][n][plane][Hp][Wp].  planes == 1: plain image rows (Hp = H).  planes == 4: parity
-// planes for a stride-2 consumer (plane = (h&1)*2 + (w&1), Hp = H/2).  Wp >= row width is the padded row
-// pitch (TMA needs rows of >= 16 bytes); pad columns are zero and never written.
-struct TransposeGeom {
-  int H, W;      // pixel grid of the tensor
-  int planes;    // 1 or 4
-  int Hp, Wp;    // rows / row pitch inside one plane
-  long cstride;  // elements per channel = N * planes * Hp * Wp
-  int dense;     // 1 if position == m (planes == 1 and Wp == W): enables the vectorised path
-};
-__device__ __forceinline__ long tpos(const TransposeGeom& g, long m) {
-  const int w = m % g.W;
-  const long r = m / g.W;
-  const int h = r % g.H;
-  const long n = r / g.H;
-  if (g.planes == 1) return (n * g.Hp + h) * g.Wp + w;
-  return ((n * 4 + (h & 1) * 2 + (w & 1)) * g.Hp + (h >> 1)) * static_cast<long>(g.Wp) + (w >> 1);
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
 // ---- forward: per-channel sum / sum of squares of the raw conv output --------------------------------------
 // grid (gx, C/64); partial[(bx*2 + stat)*C + c]
-template <bool BF16>
 __global__ void __launch_bounds__(256)
-bn_stats_partial_kernel(const uint16_t* __restrict__ raw, long M, int C, float* __restrict__ partial) {
+bn_stats_partial_kernel(const float* __restrict__ raw, long M, int C, float* __restrict__ partial) {
   __shared__ float red[2][32][65];
   const int q = threadIdx.x & 7, p = threadIdx.x >> 3;
   const int c0 = blockIdx.y * 64 + q * 8;
@@ -96,9 +94,8 @@ bn_stats_partial_kernel(const uint16_t* __restrict__ raw, long M, int C, float* 
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
   for (long m = blockIdx.x * 32L + p; m < M; m += 32L * gridDim.x) {
-    const uint4 u = *reinterpret_cast<const uint4*>(raw + m * C + c0);
     float f[8];
-    unpack8<BF16>(u, f);
+    load8f(raw + m * C + c0, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       s[e] += f[e];
@@ -146,14 +143,12 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, 
   running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
 }
 
-// ---- forward: y = clip(raw*scale + shift (+res), 0, hi) -> NHWC y and channel-major copy yT ------------------
+// ---- forward: y = clip(raw*scale + shift (+res), 0, hi), NHWC 16-bit ---------------------------------------------
 // grid (ceil(M/64), C/64)
 template <bool BF16>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
-                const uint16_t* __restrict__ res, uint16_t* __restrict__ y, uint16_t* __restrict__ yT, long M, int C,
-                float clip_hi, TransposeGeom tg) {
-  __shared__ uint16_t tile[64][kEwTilePix + 8];
+bn_apply_kernel(const float* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
+                const uint16_t* __restrict__ res, uint16_t* __restrict__ y, long M, int C, float clip_hi) {
   const int q = threadIdx.x & 7, p = threadIdx.x >> 3;
   const int c0 = blockIdx.y * 64 + q * 8;
   const long m0 = static_cast<long>(blockIdx.x) * kEwTilePix;
@@ -165,52 +160,28 @@ bn_apply_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ scal
   }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    const int lp = p + 32 * half;
-    const long m = m0 + lp;
+    const long m = m0 + p + 32 * half;
+    if (m >= M) continue;
     float f[8];
-    if (m < M) {
-      unpack8<BF16>(*reinterpret_cast<const uint4*>(raw + m * C + c0), f);
+    load8f(raw + m * C + c0, f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
-      if (res) {
-        float r[8];
-        unpack8<BF16>(*reinterpret_cast<const uint4*>(res + m * C + c0), r);
+    for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+    if (res) {
+      float r[8];
+      unpack8<BF16>(*reinterpret_cast<const uint4*>(res + m * C + c0), r);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] += r[e];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], 0.f), clip_hi);
-      const uint4 o = pack8<BF16>(f);
-      *reinterpret_cast<uint4*>(y + m * C + c0) = o;
-      if (yT) {
-        const uint16_t* h16 = reinterpret_cast<const uint16_t*>(&o);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) tile[q * 8 + e][lp] = h16[e];
-      }
+      for (int e = 0; e < 8; ++e) f[e] += r[e];
     }
-  }
-  if (!yT) return;
-  __syncthreads();
-  // channel-major write: thread -> (channel = t/4, 16 pixels = t%4)
-  const int ch = threadIdx.x >> 2, seg = threadIdx.x & 3;
-  uint16_t* dst = yT + static_cast<long>(blockIdx.y * 64 + ch) * tg.cstride;
-  if (tg.dense && m0 + kEwTilePix <= M) {
-    const uint4* src = reinterpret_cast<const uint4*>(&tile[ch][seg * 16]);
-    uint4* d = reinterpret_cast<uint4*>(dst + m0 + seg * 16);
-    d[0] = src[0];
-    d[1] = src[1];
-  } else {
-    for (int i = 0; i < 16; ++i) {
-      const long m = m0 + seg * 16 + i;
-      if (m < M) dst[tpos(tg, m)] = tile[ch][seg * 16 + i];
-    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], 0.f), clip_hi);
+    *reinterpret_cast<uint4*>(y + m * C + c0) = pack8<BF16>(f);
   }
 }
 
 // ---- backward: dbeta = sum g_z, dgamma = sum g_z * xhat, with g_z = g_y * 1[0 < y < hi] -----------------------
 template <bool BF16>
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(const uint16_t* __restrict__ gy, const uint16_t* __restrict__ y, const uint16_t* __restrict__ raw,
+bn_bwd_reduce_kernel(const uint16_t* __restrict__ gy, const uint16_t* __restrict__ y, const float* __restrict__ raw,
                      const float* __restrict__ mean, const float* __restrict__ rstd, long M, int C, float clip_hi,
                      float* __restrict__ partial) {
   __shared__ float red[2][32][65];
@@ -227,7 +198,7 @@ bn_bwd_reduce_kernel(const uint16_t* __restrict__ gy, const uint16_t* __restrict
     float g[8], yy[8], r[8];
     unpack8<BF16>(*reinterpret_cast<const uint4*>(gy + m * C + c0), g);
     unpack8<BF16>(*reinterpret_cast<const uint4*>(y + m * C + c0), yy);
-    unpack8<BF16>(*reinterpret_cast<const uint4*>(raw + m * C + c0), r);
+    load8f(raw + m * C + c0, r);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float gz = (yy[e] > 0.f && yy[e] < clip_hi) ? g[e] : 0.f;
@@ -269,14 +240,12 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
   coef[2 * C + c] = static_cast<float>(ss / static_cast<double>(M));
 }
 
-// g_raw -> G (NHWC) and GT (channel-major, plain layout); optionally g_z -> gres (NHWC) for the skip branch.
+// g_raw -> G (NHWC); optionally g_z -> gres (NHWC) for the skip branch.   grid (ceil(M/64), C/64)
 template <bool BF16>
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const uint16_t* __restrict__ gy, const uint16_t* __restrict__ y, const uint16_t* __restrict__ raw,
+bn_bwd_apply_kernel(const uint16_t* __restrict__ gy, const uint16_t* __restrict__ y, const float* __restrict__ raw,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ coef,
-                    uint16_t* __restrict__ G, uint16_t* __restrict__ GT, uint16_t* __restrict__ gres, long M, int C,
-                    float clip_hi, TransposeGeom tg) {
-  __shared__ uint16_t tile[64][kEwTilePix + 8];
+                    uint16_t* __restrict__ G, uint16_t* __restrict__ gres, long M, int C, float clip_hi) {
   const int q = threadIdx.x & 7, p = threadIdx.x >> 3;
   const int c0 = blockIdx.y * 64 + q * 8;
   const long m0 = static_cast<long>(blockIdx.x) * kEwTilePix;
@@ -291,40 +260,20 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ gy, const uint16_t* __restrict_
   }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    const int lp = p + 32 * half;
-    const long m = m0 + lp;
-    if (m < M) {
-      float g[8], yy[8], r[8];
-      unpack8<BF16>(*reinterpret_cast<const uint4*>(gy + m * C + c0), g);
-      unpack8<BF16>(*reinterpret_cast<const uint4*>(y + m * C + c0), yy);
-      unpack8<BF16>(*reinterpret_cast<const uint4*>(raw + m * C + c0), r);
-      float gz[8], gr[8];
+    const long m = m0 + p + 32 * half;
+    if (m >= M) continue;
+    float g[8], yy[8], r[8];
+    unpack8<BF16>(*reinterpret_cast<const uint4*>(gy + m * C + c0), g);
+    unpack8<BF16>(*reinterpret_cast<const uint4*>(y + m * C + c0), yy);
+    load8f(raw + m * C + c0, r);
+    float gz[8], gr[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        gz[e] = (yy[e] > 0.f && yy[e] < clip_hi) ? g[e] : 0.f;
-        gr[e] = ca[e] * (gz[e] - cb[e] - (r[e] - mu[e]) * rs[e] * cd[e]);
-      }
-      const uint4 o = pack8<BF16>(gr);
-      *reinterpret_cast<uint4*>(G + m * C + c0) = o;
-      if (gres) *reinterpret_cast<uint4*>(gres + m * C + c0) = pack8<BF16>(gz);
-      const uint16_t* h16 = reinterpret_cast<const uint16_t*>(&o);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) tile[q * 8 + e][lp] = h16[e];
+    for (int e = 0; e < 8; ++e) {
+      gz[e] = (yy[e] > 0.f && yy[e] < clip_hi) ? g[e] : 0.f;
+      gr[e] = ca[e] * (gz[e] - cb[e] - (r[e] - mu[e]) * rs[e] * cd[e]);
     }
-  }
-  __syncthreads();
-  const int ch = threadIdx.x >> 2, seg = threadIdx.x & 3;
-  uint16_t* dst = GT + static_cast<long>(blockIdx.y * 64 + ch) * tg.cstride;
-  if (tg.dense && m0 + kEwTilePix <= M) {
-    const uint4* src = reinterpret_cast<const uint4*>(&tile[ch][seg * 16]);
-    uint4* d = reinterpret_cast<uint4*>(dst + m0 + seg * 16);
-    d[0] = src[0];
-    d[1] = src[1];
-  } else {
-    for (int i = 0; i < 16; ++i) {
-      const long m = m0 + seg * 16 + i;
-      if (m < M) dst[tpos(tg, m)] = tile[ch][seg * 16 + i];
-    }
+    *reinterpret_cast<uint4*>(G + m * C + c0) = pack8<BF16>(gr);
+    if (gres) *reinterpret_cast<uint4*>(gres + m * C + c0) = pack8<BF16>(gz);
   }
 }
 

@@ -5,35 +5,53 @@
 //
 //   dW[tap][co][ci] = sum over pixels  G[pix][co] * X[pix shifted by tap][ci]
 //
-// The reduction dimension is the pixel index, so both operands are read from channel-major
-// ("transposed") 16-bit copies written by the BatchNorm kernels: GT [co][n][h][w], XT [ci][n](plane)[h][w].
-// One K-step = 64 pixels: a TMA box {kw, kh, 1, kn, rows} lands in shared memory as rows x 128 bytes,
-// i.e. the same K-major SWIZZLE_128B operand tile the forward conv uses; the tap shift and the zero
-// padding again come from TMA coordinates / out-of-bounds fill.  Work item = (tap, co tile of 128,
-// ci tile of N_TILE, K split); partial tiles are reduced with fp32 atomics into dW.
+// The reduction index is the pixel, and both tensors are NHWC (channels contiguous), so both operands are
+// "MN-major" for the tensor core: a TMA box of 128 pixels x 64 channels lands in shared memory as 128 rows of
+// 128 bytes (SWIZZLE_128B) and is consumed as one 64-wide operand atom (descriptor: leading byte offset = atom
+// stride, stride byte offset = 1024 B between 8-pixel groups, major bits = MN).  The tap shift and the zero padding
+// are TMA coordinates on the outer (w, h) dims exactly as in the forward conv, so no transposed copies exist.
+//
+// Work item = (tap, 128 output channels, N_TILE input channels, K split); partial tiles are reduced with fp32
+// atomics into dW.  Layers with 64 output channels use the swapped form (M = two taps x 64 input channels,
+// N = 64 output channels) so that the MMA still has M = 128.
 #pragma once
 #include "conv_umma.cuh"
 
 namespace dsk {
 
+constexpr int kAtomBytes = 128 * 128;  // 128 pixels x 64 channels x 2 B
+
 struct WgradParams {
+  int swapped;              // 0: A = G (2 atoms of 64 co), B = X;  1: A = X for two taps, B = G (cout == 64)
   int taps, co_tiles, ci_tiles, ksplit;
-  int cout, cin;            // real channel counts (rows beyond are TMA zero fill and are not written)
-  int chunks_w, chunks_h, chunks_n;  // K-chunk grid; chunk = box {kw, kh, kn}
-  int kw, kh, kn;
+  int cout, cin;
+  int chunks_w, chunks_h, chunks_n;  // K-chunk grid; chunk = pixel box {wt, hb, nb} of 128 pixels
+  int wt, hb, nb;
+  int16_t tap_c[kMaxTaps];  // X view: channel offset (parity column), w/h offsets, parity row
   int8_t tap_dw[kMaxTaps];
+  int8_t tap_ph[kMaxTaps];
   int8_t tap_dh[kMaxTaps];
-  int8_t tap_plane[kMaxTaps];
   float* dw;                // fp32 [tap][cout][cin], pre-zeroed
 };
 
 template <int N_TILE>
 struct WgradSmem {
-  static constexpr int kStages = (N_TILE == 64) ? 6 : (N_TILE == 128 ? 5 : 4);
-  static constexpr int kBTileBytes = N_TILE * 128;
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kBAtoms = N_TILE / 64;
+  static constexpr int kStageBytes = (2 + kBAtoms) * kAtomBytes;
+  static constexpr int kStages = (N_TILE == 64) ? 4 : 3;
   static constexpr int kTotal = kStages * kStageBytes + 256 + 1024;
 };
+
+// MN-major SWIZZLE_128B operand descriptor (see header comment)
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(kAtomBytes >> 4) << 16;  // leading byte offset: next 64-channel atom
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;        // stride byte offset: next group of 8 pixel rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 
 template <int N_TILE, bool BF16>
 __global__ void __launch_bounds__(256, 1)
@@ -41,12 +59,11 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                   const WgradParams p) {
   using S = WgradSmem<N_TILE>;
   constexpr int kStages = S::kStages;
+  constexpr int kBAtoms = S::kBAtoms;
   constexpr int kTmemCols = 2 * N_TILE;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * kATileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
@@ -57,7 +74,8 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_chunks = p.chunks_w * p.chunks_h * p.chunks_n;
-  const int num_items = p.taps * p.co_tiles * p.ci_tiles * p.ksplit;
+  const int tap_units = p.swapped ? (p.taps + 1) / 2 : p.taps;
+  const int num_items = tap_units * p.co_tiles * p.ci_tiles * p.ksplit;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmG);
@@ -83,15 +101,14 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  // item -> (tap, co tile, ci tile, K range).  K split fastest: CTAs running together share the weight tile's
-  // operands' neighbourhood in L2 and finish a (tap, co, ci) tile at about the same time.
-  auto decode = [&](int item, int& tap, int& co0, int& ci0, int& k_begin, int& k_end) {
+  // item -> (tap unit, co tile, ci tile, K range); K split fastest
+  auto decode = [&](int item, int& tu, int& co0, int& ci0, int& k_begin, int& k_end) {
     const int ks = item % p.ksplit;
     int r = item / p.ksplit;
     const int cit = r % p.ci_tiles;
     r /= p.ci_tiles;
     const int cot = r % p.co_tiles;
-    tap = r / p.co_tiles;
+    tu = r / p.co_tiles;
     co0 = cot * kTileM;
     ci0 = cit * N_TILE;
     const int per = (total_chunks + p.ksplit - 1) / p.ksplit;
@@ -104,19 +121,32 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int tap, co0, ci0, kb, ke;
-        decode(item, tap, co0, ci0, kb, ke);
-        const int dw = p.tap_dw[tap], dh = p.tap_dh[tap], plane = p.tap_plane[tap];
+        int tu, co0, ci0, kb, ke;
+        decode(item, tu, co0, ci0, kb, ke);
         for (int k = kb; k < ke; ++k) {
           const int cw = k % p.chunks_w;
           const int r = k / p.chunks_w;
           const int chh = r % p.chunks_h;
           const int cn = r / p.chunks_h;
-          const int w0 = cw * p.kw, h0 = chh * p.kh, n0 = cn * p.kn;
+          const int w0 = cw * p.wt, h0 = chh * p.hb, n0 = cn * p.nb;
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + 2 * kAtomBytes;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-          tma_load_5d(smem_a + stage * kATileBytes, &tmG, &full_bar[stage], w0, h0, 0, n0, co0);
-          tma_load_5d(smem_b + stage * S::kBTileBytes, &tmX, &full_bar[stage], w0 + dw, h0 + dh, plane, n0, ci0);
+          if (!p.swapped) {
+            tma_load_5d(sa, &tmG, &full_bar[stage], co0, w0, 0, h0, n0);
+            tma_load_5d(sa + kAtomBytes, &tmG, &full_bar[stage], co0 + 64, w0, 0, h0, n0);
+#pragma unroll
+            for (int j = 0; j < kBAtoms; ++j)
+              tma_load_5d(sb + j * kAtomBytes, &tmX, &full_bar[stage], p.tap_c[tu] + ci0 + 64 * j, w0 + p.tap_dw[tu],
+                          p.tap_ph[tu], h0 + p.tap_dh[tu], n0);
+          } else {
+            const int t0 = 2 * tu, t1 = (2 * tu + 1 < p.taps) ? 2 * tu + 1 : 2 * tu;
+            tma_load_5d(sa, &tmX, &full_bar[stage], p.tap_c[t0], w0 + p.tap_dw[t0], p.tap_ph[t0], h0 + p.tap_dh[t0], n0);
+            tma_load_5d(sa + kAtomBytes, &tmX, &full_bar[stage], p.tap_c[t1], w0 + p.tap_dw[t1], p.tap_ph[t1],
+                        h0 + p.tap_dh[t1], n0);
+            tma_load_5d(sb, &tmG, &full_bar[stage], 0, w0, 0, h0, n0);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -126,25 +156,27 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE, BF16);
+      // fp32 accumulate, both operands MN-major (bits 15 and 16)
+      constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE, BF16) | (1u << 15) | (1u << 16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int tap, co0, ci0, kb, ke;
-        decode(item, tap, co0, ci0, kb, ke);
+        int tu, co0, ci0, kb, ke;
+        decode(item, tu, co0, ci0, kb, ke);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * N_TILE;
         for (int k = kb; k < ke; ++k) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * kATileBytes));
-          const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * S::kBTileBytes));
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + 2 * kAtomBytes;
 #pragma unroll
-          for (int kk = 0; kk < kKStep / 16; ++kk)
-            umma_f16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k > kb || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk)  // 128 pixels = 8 x K16; one K16 step = 16 rows x 128 B
+            umma_f16(d_tmem, umma_desc_mn_sw128(sa + kk * 2048), umma_desc_mn_sw128(sb + kk * 2048), idesc,
+                     (k > kb || kk > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
@@ -164,13 +196,25 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      int tap, co0, ci0, kb, ke;
-      decode(item, tap, co0, ci0, kb, ke);
+      int tu, co0, ci0, kb, ke;
+      decode(item, tu, co0, ci0, kb, ke);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int co = co0 + row;
-      float* dst = p.dw + (static_cast<long>(tap) * p.cout + co) * p.cin + ci0;
-      const bool live = (co < p.cout) && (ke > kb);
+      // destination of D[row][col]
+      float* dst;
+      long col_stride;
+      bool live = ke > kb;
+      if (!p.swapped) {
+        const int co = co0 + row;
+        live = live && co < p.cout;
+        dst = p.dw + (static_cast<long>(tu) * p.cout + co) * p.cin + ci0;
+        col_stride = 1;
+      } else {
+        const int tap = 2 * tu + (row >> 6);
+        live = live && tap < p.taps;
+        dst = p.dw + static_cast<long>(tap) * p.cout * p.cin + (row & 63);  // [tap][co = col][ci = row % 64]
+        col_stride = p.cin;
+      }
 #pragma unroll 1
       for (int j = 0; j < N_TILE / 32; ++j) {
         uint32_t v[32];
@@ -178,8 +222,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         tmem_ld_wait();
         if (live) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (ci0 + j * 32 + e < p.cin) atomicAdd(dst + j * 32 + e, __uint_as_float(v[e]));
+          for (int e = 0; e < 32; ++e) atomicAdd(dst + (j * 32 + e) * col_stride, __uint_as_float(v[e]));
         }
       }
       tc_fence_before();

@@ -96,6 +96,9 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
  * gradients of every conv / BN / fc parameter, written (not accumulated) into `grads`.  Consumes the context. */
 int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx ctx, const float* grad_emb, const dsk_grads* grads,
                             void* stream);
+/* Debug / test read-back of what a train-mode forward saved: which = 0 the pre-BatchNorm conv output (fp32),
+ * 1 the post-activation tensor (16-bit), of conv layer `layer` (0..11), converted to fp32 NCHW. */
+int32_t dsk_train_ctx_read(dsk_handle h, dsk_train_ctx ctx, int32_t which, int32_t layer, float* out_nchw, void* stream);
 /* Return an unused context to the pool (forward without backward, e.g. under no_grad). */
 int32_t dsk_train_ctx_release(dsk_handle h, dsk_train_ctx ctx);
 /* fp16 operands: gradients of activations are multiplied by this power of two inside the backward and divided
@@ -116,6 +119,24 @@ int32_t dsk_get_launch_times(dsk_handle h, float* ms_out, int32_t cap, int32_t* 
 int32_t dsk_conv2d_nhwc(dsk_handle h, const void* in, const void* w_packed, const float* scale, const float* bias,
                         const void* res, void* out, int32_t B, int32_t Hin, int32_t Win, int32_t cin, int32_t cout,
                         int32_t ksize, int32_t stride, int32_t flags, float clip_hi, void* stream);
+/* Backward building blocks of dsk_rescnn_backward, exported for unit tests against torch autograd.
+ * dgrad: g_in (B,Hin,Win,cin) = d/d(input) of conv(input, w) given G (B,Hout,Wout,cout) (+ res, stride 1 only).
+ * wgrad: dw (cout,cin,k,k) fp32 = mult * d/d(w) given G and the conv input X (B,Hin,Win,cin). */
+int32_t dsk_conv2d_dgrad_nhwc(dsk_handle h, const void* G, const float* w_oihw, const void* res, void* gin, int32_t B,
+                              int32_t Hin, int32_t Win, int32_t cin, int32_t cout, int32_t ksize, int32_t stride,
+                              void* stream);
+int32_t dsk_conv2d_wgrad_nhwc(dsk_handle h, const void* G, const void* X, float* dw_oihw, int32_t B, int32_t Hin,
+                              int32_t Win, int32_t cin, int32_t cout, int32_t ksize, int32_t stride, float mult,
+                              void* stream);
+/* y = clip(BatchNorm_train(raw) (+res), 0, 20) on an NHWC tensor viewed as [M][C] (raw fp32, y/res 16-bit); writes the
+ * batch mean / rstd and updates the running statistics (model.py:59,62 in train mode + :79-80). */
+int32_t dsk_bn_act_train_forward(dsk_handle h, const float* raw, const float* gamma, const float* beta,
+                                 float* running_mean, float* running_var, const void* res, void* y, float* mean,
+                                 float* rstd, int64_t M, int32_t C, void* stream);
+/* its backward: gy -> G (w.r.t. raw), gres (w.r.t. res, may be NULL), dgamma, dbeta (x inv_scale). */
+int32_t dsk_bn_act_train_backward(dsk_handle h, const void* gy, const void* y, const float* raw, const float* gamma,
+                                  const float* mean, const float* rstd, void* G, void* gres, float* dgamma,
+                                  float* dbeta, int64_t M, int32_t C, float inv_scale, void* stream);
 int32_t dsk_pack_conv_weight(dsk_handle h, const float* w_oihw, void* w_packed, int32_t cout, int32_t cin,
                              int32_t ksize, void* stream);
 /* fp32 NCHW <-> 16-bit NHWC converters (test helpers; also used at the boundary for C>1 inputs) */

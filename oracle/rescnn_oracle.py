@@ -112,24 +112,35 @@ def l2_norm(x):
     return torch.div(x, norm.view(-1, 1).expand_as(x))
 
 
-def forward(sd, x, train: bool = False, stats_out=None, taps=None):
+def _ste(t, dtype):
+    """Round to `dtype` in the forward, identity in the backward (straight-through)."""
+    return t if dtype is None else t + (t.to(dtype).float() - t).detach()
+
+
+def forward(sd, x, train: bool = False, stats_out=None, taps=None, storage=None):
     """DeepSpeakerModel.forward, model.py:185-218. x (B,1,T,64) fp32 -> (B,E), ||.|| = 10.
-    taps: optional dict collecting per-layer activations (NCHW) keyed by conv index 0..11."""
+    taps: optional dict collecting per-layer activations (NCHW) keyed by conv index 0..11.
+    storage: None = the reference's fp32 arithmetic.  torch.float16 / torch.bfloat16 = additionally round what
+    the CUDA engine stores in 16 bit (tensor-core conv weights and every post-activation tensor; conv1, the
+    pre-BN conv outputs and the tail stay fp32).  Only used by tests that need the same ReLU/clip masks as the
+    engine to validate its backward kernels in isolation."""
+    q = lambda t: _ste(t, storage)
     h = x
     for s in range(4):
         pre = f"model.layer{s + 1}.0"
-        h = F.conv2d(h, sd[f"model.conv{s + 1}.weight"], None, 2, 2)          # model.py:187,192,197,202
-        h = clipped_relu(_bn(h, sd, f"model.bn{s + 1}", train, stats_out))     # :188-189
+        w_in = sd[f"model.conv{s + 1}.weight"]
+        h = F.conv2d(h, w_in if s == 0 else q(w_in), None, 2, 2)              # model.py:187,192,197,202
+        h = q(clipped_relu(_bn(h, sd, f"model.bn{s + 1}", train, stats_out)))  # :188-189
         if taps is not None:
             taps[3 * s] = h
         res = h                                                                # BasicBlock.forward :66-82
-        t = F.conv2d(h, sd[pre + ".conv1.weight"], None, 1, 1)
-        t = clipped_relu(_bn(t, sd, pre + ".bn1", train, stats_out))
+        t = F.conv2d(h, q(sd[pre + ".conv1.weight"]), None, 1, 1)
+        t = q(clipped_relu(_bn(t, sd, pre + ".bn1", train, stats_out)))
         if taps is not None:
             taps[3 * s + 1] = t
-        t = F.conv2d(t, sd[pre + ".conv2.weight"], None, 1, 1)
+        t = F.conv2d(t, q(sd[pre + ".conv2.weight"]), None, 1, 1)
         t = _bn(t, sd, pre + ".bn2", train, stats_out)
-        h = clipped_relu(t + res)                                              # :79-80
+        h = q(clipped_relu(t + res))                                           # :79-80
         if taps is not None:
             taps[3 * s + 2] = h
     h = h.mean(dim=2, keepdim=True)                                            # AdaptiveAvgPool2d((1,None)) :111,207
@@ -188,7 +199,7 @@ def allpairs_topk(E, labels, k: int):
     return idx, val
 
 
-def triplet_step_branch_a(sd, xa, xp, xn, margin: float, stats_out=None):
+def triplet_step_branch_a(sd, xa, xp, xn, margin: float, stats_out=None, storage=None):
     """Branch A of the training step (epoch > min_softmax_epoch), train_triplet.py:215-224:
     three separate train-mode forwards (BN statistics per call, running stats updated three times),
     triplet loss over all triplets, backward.  Returns (loss, grads dict, out_a, out_p, out_n)."""
@@ -199,7 +210,7 @@ def triplet_step_branch_a(sd, xa, xp, xn, margin: float, stats_out=None):
     outs = []
     for x in (xa, xp, xn):                                    # train_triplet.py:215
         st = {}
-        outs.append(forward(cur, x, True, st))
+        outs.append(forward(cur, x, True, st, storage=storage))
         cur.update(st)                                        # running stats carry across the three calls
     loss = triplet_margin_loss(outs[0], outs[1], outs[2], margin)   # :219
     loss.backward()                                           # :223
