@@ -193,6 +193,100 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, rank, world, local_rank):
+    """Triplet training step (restating train_triplet.py:215-224 with the drop-in classes): three train-mode
+    forwards, TripletMarginLoss, backward, ONE gradient allreduce (N > 1), Adagrad step."""
+    import torch
+    import torch.distributed as dist
+
+    from deepspeaker_pytorch_b200 import TripletMarginLoss
+    from deepspeaker_pytorch_b200.parallel import GradBucket, broadcast_parameters, path_parameters
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = 128 if args.batch == 64 else args.batch
+    T, K, W = args.frames, args.steps, args.warmup
+    model = make_model(args.dtype, dev).train()
+    broadcast_parameters(model)
+    bucket = GradBucket(path_parameters(model))
+    opt = torch.optim.Adagrad(path_parameters(model), lr=0.1, lr_decay=1e-4, weight_decay=0.0)   # train_triplet.py:70-77,378-382
+    crit = TripletMarginLoss(0.1)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    nset = 12
+    xs = [tuple(torch.randn(B, 1, T, 64, device=dev, generator=g) for _ in range(3)) for _ in range(nset)]
+
+    def step(xa, xp, xn):
+        out_a, out_p, out_n = model(xa), model(xp), model(xn)
+        loss = crit.forward(out_a, out_p, out_n)
+        bucket.zero()
+        loss.backward()
+        bucket.allreduce_mean()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(W):
+        step(*xs[i % nset])
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0.record()
+    for i in range(K):
+        loss = step(*xs[i % nset])
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    # e2e: host inputs, loss read back
+    xh = [tuple(torch.randn(B, 1, T, 64).pin_memory() for _ in range(3)) for _ in range(2)]
+    xd = [tuple(torch.empty(B, 1, T, 64, device=dev) for _ in range(3)) for _ in range(2)]
+    lh = torch.empty(1).pin_memory()
+    barrier()
+    e0.record()
+    for i in range(K):
+        for d, h_ in zip(xd[i % 2], xh[i % 2]):
+            d.copy_(h_, non_blocking=True)
+        lh.copy_(step(*xd[i % 2]).detach().reshape(1), non_blocking=True)
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms2], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = t.item()
+    if rank == 0:
+        utt = 3 * B * world * K
+        line = {
+            "metric": "utterances/sec through the triplet training step (3 forwards + loss + backward + Adagrad)",
+            "value": utt / (ms * 1e-3), "unit": "utt/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"triplet training step, batch {B} triplets per GPU (anchor/pos/neg), synthetic 64x{T} "
+                                   f"fbank, branch A (train_triplet.py:215-224), Adagrad (BASELINE configs[2]/[4])",
+                       "global_batch_triplets": B * world, "parallelism": f"dp{world}: one NCCL allreduce of 46.5 MB per step",
+                       "l2": "three fresh 5 MB input batches per step; ~2 GB of saved activations per step exceed L2"},
+            "clocks": clocks,
+            "e2e": {"value": utt / (ms2 * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": 3 * B * T * 64 * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms2 / K},
+            "tflops_whole_step": 3 * B * 6911819776 / (ms / K * 1e-3) / 1e12,
+            "last_loss": float(loss.item()),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,6 +297,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--frames", type=int, default=160)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer: batch-64 embedding inference (BASELINE configs[1], the headline metric); "
+                         "train: triplet training step, batch-128 triplets per GPU (configs[2]/[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -211,6 +308,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "train":
+        run_train(args, rank, world, local_rank)
         return
 
     import torch
