@@ -1,0 +1,324 @@
+// 3x3 stride-1 convolution on tcgen05 tensor cores with halo-tile reuse (sm_100a) — the eval-forward kernel for
+// the eight BasicBlock convs (/root/reference/model.py:47-50,58,61 used at :69,73), with the folded BatchNorm
+// affine (:59,62), the residual add (:79) and the clipped ReLU (:36-39) in the epilogue.
+//
+// Why a second conv kernel: on B200 TMA delivery is bound by request rate (~100-170 ns per box per SM whatever its
+// size, tools/micro/tma_bw.cu), and the generic kernel issues one 16 KB A box per tap.  Here:
+//   * activations live in a ZERO-PADDED NHWC layout: rows R = n*(H+1)+h+1 (row 0 and the row after every image are
+//     zero), W+1 pixels per row (column 0 is zero), so position Q = R*(W+1) + w+1 and the 3x3 neighbourhood of Q is
+//     Q + (r-1)*(W+1) + (s-1) for every pixel, including image borders (the pads are real zeros in memory);
+//   * an output tile is 128 CONSECUTIVE padded positions; its A operand for one 64-channel chunk is ONE contiguous
+//     TMA box of 128 + 2W + 4 rows (the halo), and every filter tap reads it through a UMMA descriptor whose start
+//     address is shifted by (r*(W+1)+s) rows (row-shifted SWIZZLE_128B descriptors: tools/micro/umma_shift.cu);
+//   * weights arrive as one box per filter row (3 taps x N_TILE x 64 ch); with 64 channels all 9 taps stay resident;
+//   * junk outputs (pad positions, 1/(W+1) + 1/(H+1) of the rows) are written as zeros, which keeps the pads zero.
+#pragma once
+#include "conv_umma.cuh"
+
+namespace dsk {
+
+struct HaloParams {
+  int W, H, N;            // image geometry (real pixels)
+  int q_begin;            // first position of tile 0 (= W+1: first real row)
+  int tiles_m, tiles_c;   // 128-position tiles, N_TILE channel tiles
+  int chunks;             // C / 64
+  int cout;
+  int flags;              // CONV_RESIDUAL | CONV_CLIP
+  float clip_hi;
+  const float* scale;
+  const float* bias;
+  int b_resident;         // all weight boxes of a CTA's channel tile fit the B ring: load once
+};
+
+template <int N_TILE>
+struct HaloSmem {
+  static constexpr int kAStageBytes = 25600;                 // 200 rows: 128 + 2W + 4 for W <= 34
+  static constexpr int kBStageBytes = 3 * N_TILE * 128;      // one filter row: 3 taps
+  static constexpr int kAStages = (N_TILE == 64) ? 3 : 2;
+  static constexpr int kBStages = (N_TILE == 64) ? 3 : 2;
+  static constexpr int kStagingBytes = 2 * kATileBytes;
+  static constexpr int kScaleBiasBytes = 2 * 512 * 4;
+  static constexpr int kTotal =
+      kAStages * kAStageBytes + kBStages * kBStageBytes + kStagingBytes + kScaleBiasBytes + 256 + 1024;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// tmIn : 2-D (C, positions) view of the padded input, box {64, 128 + 2W + 4}
+// tmW  : 3-D (cin, cout, 9 taps) packed weights, box {64, N_TILE, 3}
+// tmOut/tmRes : 2-D (C, positions) views of the padded output / residual, box {64, 128}
+template <int N_TILE, bool BF16>
+__global__ void __launch_bounds__(256, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                    const HaloParams p) {
+  using S = HaloSmem<N_TILE>;
+  constexpr int kAStages = S::kAStages, kBStages = S::kBStages;
+  constexpr int kTmemCols = 2 * N_TILE;
+  constexpr int kChunksOut = N_TILE / 64;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + kAStages * S::kAStageBytes;
+  uint8_t* smem_stg = smem_b + kBStages * S::kBStageBytes;
+  float* smem_scale = reinterpret_cast<float*>(smem_stg + S::kStagingBytes);
+  float* smem_bias = smem_scale + 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_scale) + S::kScaleBiasBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kAStages;
+  uint64_t* b_full = a_empty + kAStages;
+  uint64_t* b_empty = b_full + kBStages;
+  uint64_t* tmem_full = b_empty + kBStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* res_bar = tmem_empty + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pitch = p.W + 1;
+  const int halo_rows = kTileM + 2 * p.W + 4;
+  const int num_tiles = p.tiles_m * p.tiles_c;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmIn);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmOut);
+    if (p.flags & CONV_RESIDUAL) tma_prefetch_desc(&tmRes);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kAStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&res_bar[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.cout && i < 512; i += blockDim.x) {
+    smem_scale[i] = p.scale ? p.scale[i] : 1.0f;
+    smem_bias[i] = p.bias ? p.bias[i] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // channel tile slowest: a CTA's consecutive tiles (stride gridDim.x) mostly share the weight tile
+  auto decode = [&](int tile, int& c0, int& q0) {
+    const int ct = tile / p.tiles_m;
+    const int mt = tile - ct * p.tiles_m;
+    c0 = ct * N_TILE;
+    q0 = p.q_begin + mt * kTileM;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int c0, q0;
+        decode(tile, c0, q0);
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          mbar_arrive_expect_tx(&a_full[as], halo_rows * 128);
+          tma_load_2d(smem_a + as * S::kAStageBytes, &tmIn, &a_full[as], ch * 64, q0 - (p.W + 2));
+          if (++as == kAStages) {
+            as = 0;
+            aph ^= 1;
+          }
+          if (!p.b_resident || first) {
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_arrive_expect_tx(&b_full[bs], S::kBStageBytes);
+              tma_load_3d(smem_b + bs * S::kBStageBytes, &tmW, &b_full[bs], ch * 64, c0, 3 * r);
+              if (++bs == kBStages) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+        }
+        first = false;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE, BF16);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem_a + as * S::kAStageBytes);
+          for (int r = 0; r < 3; ++r) {
+            // resident weights (chunks == 1): filter row r sits in ring slot r for the whole kernel
+            const int slot = p.b_resident ? r : bs;
+            if (!p.b_resident || first) {
+              mbar_wait(&b_full[slot], bph);
+              tc_fence_after();
+            }
+            const uint32_t b_base = smem_u32(smem_b + slot * S::kBStageBytes);
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const uint64_t da = umma_desc_sw128(a_base + (r * pitch + s) * 128);
+              const uint64_t db = umma_desc_sw128(b_base + s * (N_TILE * 128));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (ch > 0 || r > 0 || s > 0 || k > 0) ? 1u : 0u);
+            }
+            if (!p.b_resident) {
+              umma_commit(&b_empty[bs]);
+              if (++bs == kBStages) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+          umma_commit(&a_empty[as]);
+          if (++as == kAStages) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        first = false;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: thread = one padded output position =====================
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const int etid = threadIdx.x - 128;
+    const bool has_res = (p.flags & CONV_RESIDUAL) != 0;
+    const bool do_clip = (p.flags & CONV_CLIP) != 0;
+    const int rows_real_end = p.N * (p.H + 1) + 1;  // first row index past the last image
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t res_phase[2] = {0, 0};
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int c0, q0;
+      decode(tile, c0, q0);
+      const int q = q0 + row;
+      const int R = q / pitch;
+      const int cc = q - R * pitch;
+      const bool junk = (cc == 0) || (R % (p.H + 1) == 0) || (R >= rows_real_end);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < kChunksOut; ++j) {
+        uint8_t* stg = smem_stg + buf * kATileBytes;
+        if (etid == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        if (has_res && etid == 0) {
+          mbar_arrive_expect_tx(&res_bar[buf], kATileBytes);
+          tma_load_2d(stg, &tmRes, &res_bar[buf], c0 + j * 64, q0);
+        }
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64;
+        tmem_ld_32x32(taddr, v0);
+        tmem_ld_32x32(taddr + 32, v1);
+        tmem_ld_wait();
+        if (has_res) {
+          mbar_wait(&res_bar[buf], res_phase[buf]);
+          res_phase[buf] ^= 1;
+        }
+        const float* sc = smem_scale + c0 + j * 64;
+        const float* bi = smem_bias + c0 + j * 64;
+        uint8_t* my_row = stg + row * 128;
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = qq * 8 + e;
+            const float a = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
+            f[e] = fmaf(a, sc[c], bi[c]);
+          }
+          uint4* slot = reinterpret_cast<uint4*>(my_row + ((qq ^ (row & 7)) << 4));
+          if (has_res) {
+            const uint4 r4 = *slot;
+            float2 t;
+            t = unpack2<BF16>(r4.x); f[0] += t.x; f[1] += t.y;
+            t = unpack2<BF16>(r4.y); f[2] += t.x; f[3] += t.y;
+            t = unpack2<BF16>(r4.z); f[4] += t.x; f[5] += t.y;
+            t = unpack2<BF16>(r4.w); f[6] += t.x; f[7] += t.y;
+          }
+          if (do_clip) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], 0.0f), p.clip_hi);
+          }
+          uint4 o;
+          o.x = pack2<BF16>(f[0], f[1]);
+          o.y = pack2<BF16>(f[2], f[3]);
+          o.z = pack2<BF16>(f[4], f[5]);
+          o.w = pack2<BF16>(f[6], f[7]);
+          if (junk) o = make_uint4(0u, 0u, 0u, 0u);  // pad positions stay zero
+          *slot = o;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (etid == 0) {
+          tma_store_2d(&tmOut, stg, c0 + j * 64, q0);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (etid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace dsk

@@ -13,6 +13,7 @@
 
 #include "../../include/dsk.h"
 #include "conv_umma.cuh"
+#include "conv3x3_halo.cuh"
 #include "loss_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "train_kernels.cuh"
@@ -106,6 +107,13 @@ struct WgradLaunch {
   int grid = 0;
 };
 
+struct HaloLaunch {
+  CUtensorMap tmIn, tmW, tmOut, tmRes;
+  dsk::HaloParams p;
+  int n_tile = 0;
+  int grid = 0;
+};
+
 struct LayerCfg {
   int cin, cout, ksize, stride;
 };
@@ -144,7 +152,8 @@ struct dsk_handle_s {
     std::vector<void*> act;  // 12 activation buffers (16-bit NHWC), index = conv index
     float* pooled = nullptr;
     float* fc_out = nullptr;
-    std::vector<ConvLaunch> conv;  // index = conv index (0 unused)
+    std::vector<ConvLaunch> conv;  // index = conv index (0 unused): the 5x5 s2 stage-entry convs
+    std::vector<HaloLaunch> halo;  // index = conv index: the 3x3 s1 block convs (padded layout)
   };
   std::map<std::pair<int, int>, Plan> plans;
   // training
@@ -478,6 +487,101 @@ int launch_wgrad(const dsk_handle_s* h, const WgradLaunch& L, cudaStream_t s) {
   return fail(DSK_ERR_INVALID, "unsupported wgrad N tile %d", L.n_tile);
 }
 
+// ---- zero-padded NHWC layout of the eval forward (see conv3x3_halo.cuh) ---------------------------------------------
+// rows: 1 leading pad + N*(H+1) (each image followed by one pad row) + slack for the last tile's halo / overrun
+long padded_positions(int N, int H, int W) {
+  const long rows = 1 + static_cast<long>(N) * (H + 1) + (128 + W + 3 + W) / (W + 1) + 2;
+  return rows * (W + 1);
+}
+size_t padded_bytes(int N, int H, int W, int C) { return static_cast<size_t>(padded_positions(N, H, W)) * C * 2; }
+const uint8_t* padded_origin(const void* base, int W, int C) {  // address of pixel (n=0, h=0, w=0)
+  return static_cast<const uint8_t*>(base) + (static_cast<size_t>(W + 1) + 1) * C * 2;
+}
+View5 padded_nhwc_view(const void* base, int N, int H, int W, int C) {
+  View5 v;
+  v.ptr = padded_origin(base, W, C);
+  v.dims[0] = C; v.dims[1] = W; v.dims[2] = 1; v.dims[3] = H; v.dims[4] = N;
+  v.str[0] = 2ull * C; v.str[1] = 2ull * (W + 1) * C; v.str[2] = 2ull * (W + 1) * C; v.str[3] = 2ull * (H + 1) * (W + 1) * C;
+  return v;
+}
+View5 padded_parity_view(const void* base, int N, int H, int W, int C) {
+  View5 v;
+  v.ptr = padded_origin(base, W, C);
+  v.dims[0] = 2ull * C; v.dims[1] = W / 2; v.dims[2] = 2; v.dims[3] = H / 2; v.dims[4] = N;
+  v.str[0] = 4ull * C; v.str[1] = 2ull * (W + 1) * C; v.str[2] = 4ull * (W + 1) * C; v.str[3] = 2ull * (H + 1) * (W + 1) * C;
+  return v;
+}
+
+// 5x5 s2 p2 conv reading and writing the padded layout (generic tap kernel, rectangular pixel tiles).
+int build_conv_s2_padded(const dsk_handle_s* h, ConvLaunch* L, const void* in, const void* wpk, const float* scale,
+                         const float* bias, void* out, int B, int Hin, int Win, int cin, int cout) {
+  TapTable tt;
+  for (int r = 0; r < 5; ++r)
+    for (int s = 0; s < 5; ++s) tt.add((s & 1) * cin, r * 5 + s, (s - 2) >> 1, r & 1, (r - 2) >> 1);
+  return build_conv_core(h, L, padded_parity_view(in, B, Hin, Win, cin), wpk, cin, cout, 25,
+                         padded_nhwc_view(out, B, Hin / 2, Win / 2, cout), nullptr, B, Hin / 2, Win / 2, tt, dsk::CONV_CLIP,
+                         20.0f, scale, bias, 0, 0);
+}
+
+// 3x3 s1 p1 conv, C -> C, on the padded layout with halo reuse.
+int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void* wpk, const float* scale,
+               const float* bias, const void* res, void* out, int N, int H, int W, int C, int flags, float clip_hi) {
+  if (C % 64 || C < 64 || C > 512) return fail(DSK_ERR_INVALID, "halo conv: C must be a multiple of 64 (got %d)", C);
+  if (W > 34) return fail(DSK_ERR_INVALID, "halo conv: W must be <= 34 (got %d)", W);
+  const bool bf = h->bf16;
+  dsk::HaloParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  p.W = W; p.H = H; p.N = N;
+  p.q_begin = W + 1;
+  const long q_end = static_cast<long>(N) * (H + 1) * (W + 1);   // one past the last real pixel position
+  p.tiles_m = static_cast<int>((q_end - p.q_begin + 127) / 128);
+  const int n_tile = C == 64 ? 64 : 128;
+  L->n_tile = n_tile;
+  p.tiles_c = C / n_tile;
+  p.chunks = C / 64;
+  p.cout = C;
+  p.flags = flags;
+  p.clip_hi = clip_hi;
+  p.scale = scale;
+  p.bias = bias;
+  p.b_resident = (C == 64) ? 1 : 0;   // 9 taps x 64 x 64 x 2 B = 72 KB stay in shared memory
+  const int num_tiles = p.tiles_m * p.tiles_c;
+  L->grid = num_tiles < h->num_sms ? num_tiles : h->num_sms;
+  const uint64_t npos = static_cast<uint64_t>(padded_positions(N, H, W));
+  uint64_t dims[2] = {(uint64_t)C, npos};
+  uint64_t str[1] = {2ull * C};
+  uint32_t box_in[2] = {64, (uint32_t)(128 + 2 * W + 4)};
+  uint32_t box_out[2] = {64, 128};
+  int rc = make_tmap(&L->tmIn, bf, in, 2, dims, str, box_in);
+  if (rc) return rc;
+  uint64_t wd[3] = {(uint64_t)C, (uint64_t)C, 9};
+  uint64_t ws[2] = {2ull * C, 2ull * C * C};
+  uint32_t wb[3] = {64, (uint32_t)n_tile, 3};
+  rc = make_tmap(&L->tmW, bf, wpk, 3, wd, ws, wb);
+  if (rc) return rc;
+  rc = make_tmap(&L->tmOut, bf, out, 2, dims, str, box_out);
+  if (rc) return rc;
+  return make_tmap(&L->tmRes, bf, (flags & dsk::CONV_RESIDUAL) ? res : out, 2, dims, str, box_out);
+}
+
+template <int N_TILE, bool BF16>
+int launch_halo_t(const HaloLaunch& L, cudaStream_t s) {
+  auto kern = dsk::conv3x3_halo_kernel<N_TILE, BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dsk::HaloSmem<N_TILE>::kTotal));
+    attr_set = true;
+  }
+  kern<<<L.grid, 256, dsk::HaloSmem<N_TILE>::kTotal, s>>>(L.tmIn, L.tmW, L.tmOut, L.tmRes, L.p);
+  KERNEL_CHECK();
+  return DSK_OK;
+}
+
+int launch_halo(const dsk_handle_s* h, const HaloLaunch& L, cudaStream_t s) {
+  if (h->bf16) return L.n_tile == 64 ? launch_halo_t<64, true>(L, s) : launch_halo_t<128, true>(L, s);
+  return L.n_tile == 64 ? launch_halo_t<64, false>(L, s) : launch_halo_t<128, false>(L, s);
+}
+
 int check_handle(dsk_handle h) {
   if (!h) return fail(DSK_ERR_INVALID, "null handle");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -506,14 +610,17 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
     return DSK_OK;
   }
   // A new shape: (re)allocate the workspace for it alone and rebuild all plans lazily.
+  // Eval activations use the zero-padded NHWC layout (conv3x3_halo.cuh); pads are zeroed here once and are
+  // never overwritten with anything but zeros.
   size_t bytes = 0;
   size_t off[DSK_NUM_CONV];
   for (int i = 0; i < DSK_NUM_CONV; ++i) {
     int H, W, C;
     act_shape(i, T, H, W, C);
     off[i] = bytes;
-    bytes += ((static_cast<size_t>(B) * H * W * C * 2 + 1023) / 1024) * 1024;
+    bytes += ((padded_bytes(B, H, W, C) + 1023) / 1024) * 1024;
   }
+  const size_t act_bytes = bytes;
   const size_t off_pooled = bytes;
   bytes += static_cast<size_t>(B) * 2048 * 4;
   const size_t off_fc = bytes;
@@ -527,8 +634,11 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
     CUDA_TRY(cudaMalloc(&h->ws, bytes));
     h->ws_bytes = bytes;
   } else {
-    // one workspace is shared by all shapes; descriptors of other shapes stay valid (same base pointer)
+    // the workspace is shared by all shapes, but the pad positions differ per shape: plans of other shapes would
+    // find non-zero pads after this one ran, so only one shape is cached at a time
+    h->plans.clear();
   }
+  CUDA_TRY(cudaMemset(h->ws, 0, act_bytes));
   dsk_handle_s::Plan pl;
   pl.B = B;
   pl.T = T;
@@ -538,15 +648,22 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
   pl.pooled = reinterpret_cast<float*>(base + off_pooled);
   pl.fc_out = reinterpret_cast<float*>(base + off_fc);
   pl.conv.resize(DSK_NUM_CONV);
+  pl.halo.resize(DSK_NUM_CONV);
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
     const LayerCfg c = layer_cfg(i);
     int Hi, Wi, Ci;
     act_shape(i - 1, T, Hi, Wi, Ci);  // input of conv i is activation i-1
     const int k = i % 3;
-    const void* res = (k == 2) ? pl.act[i - 2] : nullptr;  // block output adds the block input
-    const int flags = dsk::CONV_CLIP | (k == 2 ? dsk::CONV_RESIDUAL : 0);
-    int rc = build_conv(h, &pl.conv[i], pl.act[i - 1], h->wpk[i], h->scale[i], h->bias[i], res, pl.act[i], B, Hi, Wi,
-                        c.cin, c.cout, c.ksize, c.stride, flags, 20.0f);
+    int rc;
+    if (k == 0) {
+      rc = build_conv_s2_padded(h, &pl.conv[i], pl.act[i - 1], h->wpk[i], h->scale[i], h->bias[i], pl.act[i], B, Hi, Wi,
+                                c.cin, c.cout);
+    } else {
+      const void* res = (k == 2) ? pl.act[i - 2] : nullptr;  // block output adds the block input
+      const int flags = dsk::CONV_CLIP | (k == 2 ? dsk::CONV_RESIDUAL : 0);
+      rc = build_halo(h, &pl.halo[i], pl.act[i - 1], h->wpk[i], h->scale[i], h->bias[i], res, pl.act[i], B, Hi, Wi, c.cin,
+                      flags, 20.0f);
+    }
     if (rc) return rc;
   }
   auto ins = h->plans.emplace(key, std::move(pl));
@@ -702,14 +819,14 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
     const int hout = T / 2;
     const int blocks = B * ((hout + 7) / 8);
     if (h->bf16)
-      dsk::conv1_kernel<true><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->scale[0], h->bias[0], (uint16_t*)pl->act[0], T, 1, 20.0f);
+      dsk::conv1_kernel<true><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->scale[0], h->bias[0], (uint16_t*)pl->act[0], T, 1, 20.0f, 1);
     else
-      dsk::conv1_kernel<false><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->scale[0], h->bias[0], (uint16_t*)pl->act[0], T, 1, 20.0f);
+      dsk::conv1_kernel<false><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->scale[0], h->bias[0], (uint16_t*)pl->act[0], T, 1, 20.0f, 1);
     KERNEL_CHECK();
     mark();
   }
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
-    rc = launch_conv(h, pl->conv[i], s);
+    rc = (i % 3 == 0) ? launch_conv(h, pl->conv[i], s) : launch_halo(h, pl->halo[i], s);
     if (rc) return rc;
     mark();
   }
@@ -717,9 +834,9 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
   {
     const int H4 = T / 16, WC = 4 * 512;
     if (h->bf16)
-      dsk::pool_time_kernel<true><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC);
+      dsk::pool_time_kernel<true><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC, 512, 1);
     else
-      dsk::pool_time_kernel<false><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC);
+      dsk::pool_time_kernel<false><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC, 512, 1);
     KERNEL_CHECK();
     mark();
     static bool fc_attr = false;
@@ -894,7 +1011,7 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
     const long M = static_cast<long>(B) * H * W;
     if (i == 0) {
       const int blocks = B * ((T / 2 + 7) / 8);
-      dsk::conv1_kernel<false, true><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->ones, h->zeros, c->raw[0], T, 0, 0.f);
+      dsk::conv1_kernel<false, true><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->ones, h->zeros, c->raw[0], T, 0, 0.f, 0);
       KERNEL_CHECK();
     } else {
       rc = launch_conv(h, c->conv[i], s);
@@ -920,8 +1037,8 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
   }
   {
     const int H4 = T / 16, WC = 4 * 512;
-    if (bf) dsk::pool_time_kernel<true><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC);
-    else dsk::pool_time_kernel<false><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC);
+    if (bf) dsk::pool_time_kernel<true><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC, 512, 0);
+    else dsk::pool_time_kernel<false><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC, 512, 0);
     KERNEL_CHECK();
     const int fc_smem = 8 * 2048 * 4;
     CUDA_TRY(cudaFuncSetAttribute(dsk::fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem));
@@ -1160,6 +1277,21 @@ int32_t dsk_bn_act_train_backward(dsk_handle h, const void* gy, const void* y, c
   CUDA_TRY(cudaFreeAsync(tmp, s));
   return DSK_OK;
 }
+
+int32_t dsk_conv3x3_padded(dsk_handle h, const void* in, const void* w_packed, const float* scale, const float* bias,
+                           const void* res, void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t flags,
+                           float clip_hi, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!in || !w_packed || !out) return fail(DSK_ERR_INVALID, "dsk_conv3x3_padded: null pointer");
+  if ((flags & dsk::CONV_RESIDUAL) && !res) return fail(DSK_ERR_INVALID, "dsk_conv3x3_padded: residual flag without res");
+  HaloLaunch L;
+  rc = build_halo(h, &L, in, w_packed, scale, bias, res, out, N, H, W, C, flags, clip_hi);
+  if (rc) return rc;
+  return launch_halo(h, L, static_cast<cudaStream_t>(stream));
+}
+
+int64_t dsk_padded_positions(int32_t N, int32_t H, int32_t W) { return padded_positions(N, H, W); }
 
 int32_t dsk_conv2d_nhwc(dsk_handle h, const void* in, const void* w_packed, const float* scale, const float* bias,
                         const void* res, void* out, int32_t B, int32_t Hin, int32_t Win, int32_t cin, int32_t cout,

@@ -61,7 +61,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 template <bool BF16, bool OUT_F32 = false>
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]*/, const float* __restrict__ scale,
-             const float* __restrict__ bias, void* __restrict__ out, int T, int do_clip, float clip_hi) {
+             const float* __restrict__ bias, void* __restrict__ out, int T, int do_clip, float clip_hi, int padded) {
   constexpr int WIN = 64, WOUT = 32, ROWS = 8, PATCH_ROWS = 2 * ROWS + 3, PATCH_W = WIN + 4;
   __shared__ float patch[PATCH_ROWS][PATCH_W];
   __shared__ float wsm[64 * 25];
@@ -89,7 +89,9 @@ conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]
   uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
   const int oh = h0 + warp;  // one output row per warp
   if (oh >= hout) return;
-  const long pix0 = (static_cast<long>(n) * hout + oh) * WOUT;
+  // padded NHWC layout (conv3x3_halo.cuh): row n*(H+1)+h+1, W+1 pixels per row, column 0 is the zero pad
+  const long pix0 = padded ? (static_cast<long>(n) * (hout + 1) + oh + 1) * (WOUT + 1) + 1
+                           : (static_cast<long>(n) * hout + oh) * WOUT;
 #pragma unroll 2
   for (int ow = 0; ow < WOUT; ++ow) {
     float a0 = 0.f, a1 = 0.f;
@@ -123,19 +125,22 @@ conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]
 // ---------------------------------------------------------------------------------------------
 template <bool BF16>
 __global__ void __launch_bounds__(256)
-pool_time_kernel(const uint16_t* __restrict__ act, float* __restrict__ pooled, int H, int WC) {
+pool_time_kernel(const uint16_t* __restrict__ act, float* __restrict__ pooled, int H, int WC, int C, int padded) {
   // grid (B, WC/512): thread = 2 adjacent channels (one 32-bit load per time step), loads independent in h
   const int b = blockIdx.x;
   const int i = blockIdx.y * 256 + threadIdx.x;  // index of the channel pair
   if (i >= WC / 2) return;
-  const uint32_t* a = reinterpret_cast<const uint32_t*>(act + static_cast<long>(b) * H * WC) + i;
+  // dense: rows of W*C; padded layout: rows of (W+1)*C with a leading zero pixel, images H+1 rows apart, first row is a pad
+  const long row_pitch = padded ? (WC + C) / 2 : WC / 2;
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(act) +
+                      (padded ? (static_cast<long>(b) * (H + 1) + 1) * row_pitch + C / 2 : static_cast<long>(b) * H * row_pitch) + i;
   const float inv = 1.0f / static_cast<float>(H);
   float s0 = 0.f, s1 = 0.f;
   int h = 0;
   for (; h + 4 <= H; h += 4) {
     uint32_t u[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) u[j] = a[static_cast<long>(h + j) * (WC / 2)];
+    for (int j = 0; j < 4; ++j) u[j] = a[static_cast<long>(h + j) * row_pitch];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 v = unpack2<BF16>(u[j]);
@@ -144,7 +149,7 @@ pool_time_kernel(const uint16_t* __restrict__ act, float* __restrict__ pooled, i
     }
   }
   for (; h < H; ++h) {
-    const float2 v = unpack2<BF16>(a[static_cast<long>(h) * (WC / 2)]);
+    const float2 v = unpack2<BF16>(a[static_cast<long>(h) * row_pitch]);
     s0 += v.x;
     s1 += v.y;
   }

@@ -137,6 +137,13 @@ int32_t dsk_bn_act_train_forward(dsk_handle h, const float* raw, const float* ga
 int32_t dsk_bn_act_train_backward(dsk_handle h, const void* gy, const void* y, const float* raw, const float* gamma,
                                   const float* mean, const float* rstd, void* G, void* gres, float* dgamma,
                                   float* dbeta, int64_t M, int32_t C, float inv_scale, void* stream);
+/* The eval forward's 3x3 s1 conv (C -> C) on the zero-padded NHWC layout with halo reuse (csrc/conv3x3_halo.cuh):
+ * tensors are [dsk_padded_positions(N,H,W)][C] 16-bit, pixel (n,h,w) at position (n*(H+1)+h+1)*(W+1) + w+1, all
+ * other positions zero.  Exported for unit tests.  W <= 34. */
+int32_t dsk_conv3x3_padded(dsk_handle h, const void* in, const void* w_packed, const float* scale, const float* bias,
+                           const void* res, void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t flags,
+                           float clip_hi, void* stream);
+int64_t dsk_padded_positions(int32_t N, int32_t H, int32_t W);
 int32_t dsk_pack_conv_weight(dsk_handle h, const float* w_oihw, void* w_packed, int32_t cout, int32_t cin,
                              int32_t ksize, void* stream);
 /* fp32 NCHW <-> 16-bit NHWC converters (test helpers; also used at the boundary for C>1 inputs) */
