@@ -4,4 +4,6 @@ TripletMarginLoss and PairwiseDistance, backed by hand-written sm_100a CUDA behi
 from .model import (DeepSpeakerModel, PairwiseDistance, TripletMarginLoss, allpairs_topk,  # noqa: F401
                     select_hard_triplets)
 
-__all__ = ["DeepSpeakerModel", "PairwiseDistance", "TripletMarginLoss", "select_hard_triplets", "allpairs_topk"]
+from .pipeline import EmbeddingPipeline  # noqa: F401,E402
+
+__all__ = ["EmbeddingPipeline", "DeepSpeakerModel", "PairwiseDistance", "TripletMarginLoss", "select_hard_triplets", "allpairs_topk"]

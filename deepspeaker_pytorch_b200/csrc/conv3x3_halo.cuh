@@ -28,7 +28,15 @@ struct HaloParams {
   const float* scale;
   const float* bias;
   int b_resident;         // all weight boxes of a CTA's channel tile fit the B ring: load once
+  unsigned pitch_magic, img_magic;  // floor(2^32/d)+1 for d = W+1 and H+1: q/d == __umulhi(q, magic) for q < 2^32/d
+  long long* trace;       // debug: per-role clock64 stamps of CTA 0 (nullptr = off); [role 0..2][512]
 };
+
+// role: 0 producer, 1 MMA, 2 epilogue
+#define DSK_TRACE(role, idx)                                                                  \
+  do {                                                                                        \
+    if (p.trace && blockIdx.x == 0 && (idx) < 512) p.trace[(role) * 512 + (idx)] = clock64(); \
+  } while (0)
 
 template <int N_TILE>
 struct HaloSmem {
@@ -37,9 +45,11 @@ struct HaloSmem {
   static constexpr int kAStages = (N_TILE == 64) ? 3 : 2;
   static constexpr int kBStages = (N_TILE == 64) ? 3 : 2;
   static constexpr int kStagingBytes = 2 * kATileBytes;
+  static constexpr int kResBytes = 2 * kATileBytes;          // residual tiles prefetched by their own warp
   static constexpr int kScaleBiasBytes = 2 * 512 * 4;
+  static constexpr int kAccStages = 4;                       // TMEM accumulators: 4 x N_TILE <= 512 columns
   static constexpr int kTotal =
-      kAStages * kAStageBytes + kBStages * kBStageBytes + kStagingBytes + kScaleBiasBytes + 256 + 1024;
+      kAStages * kAStageBytes + kBStages * kBStageBytes + kStagingBytes + kResBytes + kScaleBiasBytes + 256 + 1024;
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
@@ -59,14 +69,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 // tmIn : 2-D (C, positions) view of the padded input, box {64, 128 + 2W + 4}
 // tmW  : 3-D (cin, cout, 9 taps) packed weights, box {64, N_TILE, 3}
 // tmOut/tmRes : 2-D (C, positions) views of the padded output / residual, box {64, 128}
+constexpr int kHaloThreads = 384;  // 4 control warps + 8 epilogue warps (two per scheduler)
+
 template <int N_TILE, bool BF16>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kHaloThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                     const HaloParams p) {
   using S = HaloSmem<N_TILE>;
   constexpr int kAStages = S::kAStages, kBStages = S::kBStages;
-  constexpr int kTmemCols = 2 * N_TILE;
+  constexpr int kAcc = S::kAccStages;
+  constexpr int kTmemCols = kAcc * N_TILE;
   constexpr int kChunksOut = N_TILE / 64;
 
   extern __shared__ uint8_t smem_raw[];
@@ -74,7 +87,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + kAStages * S::kAStageBytes;
   uint8_t* smem_stg = smem_b + kBStages * S::kBStageBytes;
-  float* smem_scale = reinterpret_cast<float*>(smem_stg + S::kStagingBytes);
+  uint8_t* smem_res = smem_stg + S::kStagingBytes;
+  float* smem_scale = reinterpret_cast<float*>(smem_res + S::kResBytes);
   float* smem_bias = smem_scale + 512;
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_scale) + S::kScaleBiasBytes);
   uint64_t* a_full = bars;
@@ -82,12 +96,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   uint64_t* b_full = a_empty + kAStages;
   uint64_t* b_empty = b_full + kBStages;
   uint64_t* tmem_full = b_empty + kBStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_empty + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* tmem_empty = tmem_full + kAcc;
+  uint64_t* res_full = tmem_empty + kAcc;
+  uint64_t* res_empty = res_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int pitch = p.W + 1;
   const int halo_rows = kTileM + 2 * p.W + 4;
   const int num_tiles = p.tiles_m * p.tiles_c;
@@ -107,10 +123,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
-      mbar_init(&res_bar[i], 1);
+      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&res_full[i], 1);
+      mbar_init(&res_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -126,6 +145,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above touched only parameters; activations of the previous kernel are read/written below
 
   // channel tile slowest: a CTA's consecutive tiles (stride gridDim.x) mostly share the weight tile
   auto decode = [&](int tile, int& c0, int& q0) {
@@ -136,95 +156,135 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   };
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      bool first = true;
+    // ===================== TMA producer (warp-converged loop, one elected lane issues) =====================
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    bool first = true;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int c0, q0;
+      decode(tile, c0, q0);
+      for (int ch = 0; ch < p.chunks; ++ch) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&a_full[as], halo_rows * 128);
+          tma_load_2d(smem_a + as * S::kAStageBytes, &tmIn, &a_full[as], ch * 64, q0 - (p.W + 2));
+          DSK_TRACE(0, tcount);
+          ++tcount;
+        }
+        __syncwarp();
+        if (++as == kAStages) {
+          as = 0;
+          aph ^= 1;
+        }
+        if (!p.b_resident || first) {
+          for (int r = 0; r < 3; ++r) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&b_full[bs], S::kBStageBytes);
+              tma_load_3d(smem_b + bs * S::kBStageBytes, &tmW, &b_full[bs], ch * 64, c0, 3 * r);
+            }
+            __syncwarp();
+            if (++bs == kBStages) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+      first = false;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-converged loop, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE, BF16);
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    bool first = true;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      if (lane == 0) DSK_TRACE(1, tcount * 4 + 0);
+      const uint32_t d_tmem = tmem_base + acc * N_TILE;
+      for (int ch = 0; ch < p.chunks; ++ch) {
+        mbar_wait(&a_full[as], aph);
+        tc_fence_after();
+        if (lane == 0 && ch == 0) DSK_TRACE(1, tcount * 4 + 1);
+        const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a + as * S::kAStageBytes));
+        for (int r = 0; r < 3; ++r) {
+          // resident weights (chunks == 1): filter row r sits in ring slot r for the whole kernel
+          const int slot = p.b_resident ? r : bs;
+          if (!p.b_resident || first) {
+            mbar_wait(&b_full[slot], bph);
+            tc_fence_after();
+          }
+          if (elect_one_sync()) {
+            const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b + slot * S::kBStageBytes));
+            // tap (r, s): A rows shifted by r*(W+1)+s (x 128 B = +8 per row in the addr>>4 field); B tap s is
+            // N_TILE*128 B further; K16 step = +2
+            const uint64_t da_r = da0 + static_cast<uint64_t>(r * pitch) * 8;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(d_tmem, da_r + (s * 8 + 2 * k), db0 + (s * (N_TILE * 8) + 2 * k), idesc,
+                         (ch > 0 || r > 0 || s > 0 || k > 0) ? 1u : 0u);
+            }
+            if (!p.b_resident) umma_commit(&b_empty[bs]);
+            if (r == 2) {
+              umma_commit(&a_empty[as]);
+              if (ch == p.chunks - 1) umma_commit(&tmem_full[acc]);
+            }
+          }
+          __syncwarp();
+          if (!p.b_resident) {
+            if (++bs == kBStages) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+        if (++as == kAStages) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+      if (lane == 0) DSK_TRACE(1, tcount * 4 + 2);
+      ++tcount;
+      if (++acc == kAcc) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      first = false;
+    }
+  } else if (warp == 3) {
+    // ===================== residual prefetcher: one 128 x 64 tile per output chunk, two buffers =====================
+    if (p.flags & CONV_RESIDUAL) {
+      int rb = 0;
+      uint32_t rph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int c0, q0;
         decode(tile, c0, q0);
-        for (int ch = 0; ch < p.chunks; ++ch) {
-          mbar_wait(&a_empty[as], aph ^ 1);
-          mbar_arrive_expect_tx(&a_full[as], halo_rows * 128);
-          tma_load_2d(smem_a + as * S::kAStageBytes, &tmIn, &a_full[as], ch * 64, q0 - (p.W + 2));
-          if (++as == kAStages) {
-            as = 0;
-            aph ^= 1;
+        for (int j = 0; j < kChunksOut; ++j) {
+          mbar_wait(&res_empty[rb], rph ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&res_full[rb], kATileBytes);
+            tma_load_2d(smem_res + rb * kATileBytes, &tmRes, &res_full[rb], c0 + j * 64, q0);
           }
-          if (!p.b_resident || first) {
-            for (int r = 0; r < 3; ++r) {
-              mbar_wait(&b_empty[bs], bph ^ 1);
-              mbar_arrive_expect_tx(&b_full[bs], S::kBStageBytes);
-              tma_load_3d(smem_b + bs * S::kBStageBytes, &tmW, &b_full[bs], ch * 64, c0, 3 * r);
-              if (++bs == kBStages) {
-                bs = 0;
-                bph ^= 1;
-              }
-            }
+          __syncwarp();
+          if (++rb == 2) {
+            rb = 0;
+            rph ^= 1;
           }
         }
-        first = false;
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE, BF16);
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      bool first = true;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_TILE;
-        for (int ch = 0; ch < p.chunks; ++ch) {
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem_a + as * S::kAStageBytes);
-          for (int r = 0; r < 3; ++r) {
-            // resident weights (chunks == 1): filter row r sits in ring slot r for the whole kernel
-            const int slot = p.b_resident ? r : bs;
-            if (!p.b_resident || first) {
-              mbar_wait(&b_full[slot], bph);
-              tc_fence_after();
-            }
-            const uint32_t b_base = smem_u32(smem_b + slot * S::kBStageBytes);
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              const uint64_t da = umma_desc_sw128(a_base + (r * pitch + s) * 128);
-              const uint64_t db = umma_desc_sw128(b_base + s * (N_TILE * 128));
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (ch > 0 || r > 0 || s > 0 || k > 0) ? 1u : 0u);
-            }
-            if (!p.b_resident) {
-              umma_commit(&b_empty[bs]);
-              if (++bs == kBStages) {
-                bs = 0;
-                bph ^= 1;
-              }
-            }
-          }
-          umma_commit(&a_empty[as]);
-          if (++as == kAStages) {
-            as = 0;
-            aph ^= 1;
-          }
-        }
-        umma_commit(&tmem_full[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
-        first = false;
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: thread = one padded output position =====================
-    const int ew = warp - 4;
+    // ===================== epilogue: 8 warps; thread = one padded output position x 32 of the 64 channels ==========
+    const int ew = (warp - 4) & 3;          // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int half = (warp - 4) >> 2;       // which 32 columns of each 64-column chunk
     const int row = ew * 32 + lane;
     const int etid = threadIdx.x - 128;
     const bool has_res = (p.flags & CONV_RESIDUAL) != 0;
@@ -232,50 +292,54 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     const int rows_real_end = p.N * (p.H + 1) + 1;  // first row index past the last image
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t res_phase[2] = {0, 0};
+    int rb = 0;
+    uint32_t rph = 0;
     int buf = 0;
+    int ecount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int c0, q0;
       decode(tile, c0, q0);
       const int q = q0 + row;
-      const int R = q / pitch;
+      const int R = static_cast<int>(__umulhi(static_cast<unsigned>(q), p.pitch_magic));
       const int cc = q - R * pitch;
-      const bool junk = (cc == 0) || (R % (p.H + 1) == 0) || (R >= rows_real_end);
+      const int img = static_cast<int>(__umulhi(static_cast<unsigned>(R), p.img_magic));
+      const bool junk = (cc == 0) || (R - img * (p.H + 1) == 0) || (R >= rows_real_end);
+      if (etid == 0) DSK_TRACE(2, ecount * 8 + 0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (etid == 0) DSK_TRACE(2, ecount * 8 + 1);
 #pragma unroll 1
       for (int j = 0; j < kChunksOut; ++j) {
         uint8_t* stg = smem_stg + buf * kATileBytes;
         if (etid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        if (has_res && etid == 0) {
-          mbar_arrive_expect_tx(&res_bar[buf], kATileBytes);
-          tma_load_2d(stg, &tmRes, &res_bar[buf], c0 + j * 64, q0);
-        }
-        uint32_t v0[32], v1[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64;
-        tmem_ld_32x32(taddr, v0);
-        tmem_ld_32x32(taddr + 32, v1);
+        named_bar_sync(1, 256);
+        if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 2);
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64 + half * 32, v);
         tmem_ld_wait();
-        if (has_res) {
-          mbar_wait(&res_bar[buf], res_phase[buf]);
-          res_phase[buf] ^= 1;
-        }
-        const float* sc = smem_scale + c0 + j * 64;
-        const float* bi = smem_bias + c0 + j * 64;
+        if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 3);
+        if (has_res) mbar_wait(&res_full[rb], rph);
+        if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 4);
+        const uint8_t* res_row = smem_res + rb * kATileBytes + row * 128;
+        const float* sc = smem_scale + c0 + j * 64 + half * 32;
+        const float* bi = smem_bias + c0 + j * 64 + half * 32;
         uint8_t* my_row = stg + row * 128;
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) {
+        for (int qq = 0; qq < 4; ++qq) {
           float f[8];
+          // per-channel scale / bias: four broadcast 16-byte shared-memory loads for 8 channels
+          const float4 s0 = *reinterpret_cast<const float4*>(sc + qq * 8);
+          const float4 s1 = *reinterpret_cast<const float4*>(sc + qq * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(bi + qq * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bi + qq * 8 + 4);
+          const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float biv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = qq * 8 + e;
-            const float a = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
-            f[e] = fmaf(a, sc[c], bi[c]);
-          }
-          uint4* slot = reinterpret_cast<uint4*>(my_row + ((qq ^ (row & 7)) << 4));
+          for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[qq * 8 + e]), scv[e], biv[e]);
+          const int chunk16 = ((half * 4 + qq) ^ (row & 7)) << 4;  // 16-byte slot inside the swizzled 128-byte row
+          uint4* slot = reinterpret_cast<uint4*>(my_row + chunk16);
           if (has_res) {
-            const uint4 r4 = *slot;
+            const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + chunk16);
             float2 t;
             t = unpack2<BF16>(r4.x); f[0] += t.x; f[1] += t.y;
             t = unpack2<BF16>(r4.y); f[2] += t.x; f[3] += t.y;
@@ -294,18 +358,30 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           if (junk) o = make_uint4(0u, 0u, 0u, 0u);  // pad positions stay zero
           *slot = o;
         }
+        if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 5);
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        if (has_res) {  // residual buffer consumed: hand it back to the prefetcher
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&res_empty[rb]);
+          if (++rb == 2) {
+            rb = 0;
+            rph ^= 1;
+          }
+        }
+        named_bar_sync(1, 256);
         if (etid == 0) {
           tma_store_2d(&tmOut, stg, c0 + j * 64, q0);
           tma_store_commit();
         }
+        if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 6);
         buf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) {
+      if (etid == 0) DSK_TRACE(2, ecount * 8 + 7);
+      ++ecount;
+      if (++acc == kAcc) {
         acc = 0;
         acc_phase ^= 1;
       }

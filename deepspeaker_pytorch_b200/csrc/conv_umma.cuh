@@ -50,27 +50,33 @@ struct ConvParams {
   int8_t tap_dh[kMaxTaps];
 };
 
+constexpr int kConvThreads = 384;  // 4 control warps (TMA, MMA, TMEM alloc, residual prefetch) + 8 epilogue warps
+
 template <int N_TILE>
 struct ConvSmem {
-  static constexpr int kStages = (N_TILE == 64) ? 6 : (N_TILE == 128 ? 5 : 3);
+  static constexpr int kStages = (N_TILE == 64) ? 6 : (N_TILE == 128 ? 4 : 3);
   static constexpr int kBTileBytes = N_TILE * 128;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStagingBytes = 2 * kATileBytes;  // two 128x64 16-bit output chunks
+  static constexpr int kStagingBytes = 2 * kATileBytes;  // two 128-row x 128-byte output chunks
+  static constexpr int kResBytes = 2 * kATileBytes;      // residual tiles, prefetched by their own warp
   static constexpr int kScaleBiasBytes = 2 * 512 * 4;
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kScaleBiasBytes + kBarBytes + 1024;
+  static constexpr int kAccStages = (N_TILE == 256) ? 2 : 4;  // TMEM accumulators (<= 512 columns)
+  static constexpr int kTotal =
+      kStages * kStageBytes + kStagingBytes + kResBytes + kScaleBiasBytes + kBarBytes + 1024;
 };
 
 // OUT_F32: the epilogue stores fp32 (no residual / clip): used for the pre-BatchNorm conv output of the
 // train-mode forward, which must not be rounded to 16 bit before the batch statistics are applied.
 template <int N_TILE, bool BF16, bool OUT_F32 = false>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const ConvParams p) {
   using S = ConvSmem<N_TILE>;
   constexpr int kStages = S::kStages;
-  constexpr int kTmemCols = (2 * N_TILE <= 32) ? 32 : 2 * N_TILE;  // double-buffered accumulator
+  constexpr int kAcc = S::kAccStages;
+  constexpr int kTmemCols = kAcc * N_TILE;
   constexpr int kChunks = N_TILE / 64;
 
   extern __shared__ uint8_t smem_raw[];
@@ -78,18 +84,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kATileBytes;
   uint8_t* smem_stg = smem + kStages * S::kStageBytes;
-  float* smem_scale = reinterpret_cast<float*>(smem_stg + S::kStagingBytes);
+  uint8_t* smem_res = smem_stg + S::kStagingBytes;
+  float* smem_scale = reinterpret_cast<float*>(smem_res + S::kResBytes);
   float* smem_bias = smem_scale + 512;
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_scale) + S::kScaleBiasBytes);
   uint64_t* full_bar = bars;                  // [kStages]
   uint64_t* empty_bar = bars + kStages;       // [kStages]
-  uint64_t* tmem_full = bars + 2 * kStages;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint64_t* res_bar = tmem_empty + 2;         // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* tmem_full = bars + 2 * kStages;   // [kAcc]
+  uint64_t* tmem_empty = tmem_full + kAcc;    // [kAcc]
+  uint64_t* res_full = tmem_empty + kAcc;     // [2]
+  uint64_t* res_empty = res_full + 2;         // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   const int ksteps = p.taps * p.cin_chunks;
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -107,10 +116,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
-      mbar_init(&res_bar[i], 1);
+      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&res_full[i], 1);
+      mbar_init(&res_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -126,6 +138,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above touched only parameters; activations of the previous kernel are read/written below
 
   // tile -> coordinates. Tile order: cout tile fastest so CTAs running concurrently share the A tile in L2.
   auto decode = [&](int tile, int& c0, int& w0, int& h0, int& n0) {
@@ -142,43 +155,44 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   };
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int c0, w0, h0, n0;
-        decode(tile, c0, w0, h0, n0);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const int tap = ks / p.cin_chunks;
-          const int ch = ks - tap * p.cin_chunks;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================== TMA producer (warp-converged loop, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int c0, w0, h0, n0;
+      decode(tile, c0, w0, h0, n0);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int tap = ks / p.cin_chunks;
+        const int ch = ks - tap * p.cin_chunks;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
           tma_load_5d(smem_a + stage * kATileBytes, &tmA, &full_bar[stage], p.tap_c[tap] + ch * kKStep,
                       w0 + p.tap_dw[tap], p.tap_ph[tap], h0 + p.tap_dh[tap], n0);
           tma_load_3d(smem_b + stage * S::kBTileBytes, &tmB, &full_bar[stage], ch * kKStep, c0, p.tap_w[tap]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE, BF16);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (warp-converged loop, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE, BF16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * N_TILE;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_TILE;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * kATileBytes));
           const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * S::kBTileBytes));
 #pragma unroll
@@ -187,131 +201,150 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (ks > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (ks == ksteps - 1) umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&tmem_full[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == kAcc) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== residual prefetcher: one 128 x 64 tile per output chunk, two buffers =====================
+    if (!OUT_F32 && (p.flags & CONV_RESIDUAL)) {
+      int rb = 0;
+      uint32_t rph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int c0, w0, h0, n0;
+        decode(tile, c0, w0, h0, n0);
+        for (int j = 0; j < kChunks; ++j) {
+          mbar_wait(&res_empty[rb], rph ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&res_full[rb], kATileBytes);
+            tma_load_5d(smem_res + rb * kATileBytes, &tmRes, &res_full[rb], p.out_c_base + c0 + j * 64, w0, p.out_ph, h0, n0);
+          }
+          __syncwarp();
+          if (++rb == 2) {
+            rb = 0;
+            rph ^= 1;
+          }
         }
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (128 threads, thread = one output pixel row) =====================
-    const int ew = warp - 4;               // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const int row = ew * 32 + lane;        // row of the 128-row tile
+    // ===================== epilogue: 8 warps; thread = one output pixel x 32 of the 64 channels of a chunk =========
+    const int ew = (warp - 4) & 3;          // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int half = (warp - 4) >> 2;       // which 32 accumulator columns of each 64-column group
+    const int row = ew * 32 + lane;         // row of the 128-row tile
     const int etid = threadIdx.x - 128;
     const bool has_res = (p.flags & CONV_RESIDUAL) != 0;
     const bool do_clip = (p.flags & CONV_CLIP) != 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t res_phase[2] = {0, 0};
+    int rb = 0;
+    uint32_t rph = 0;
     int buf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int c0, w0, h0, n0;
       decode(tile, c0, w0, h0, n0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if constexpr (OUT_F32) {
 #pragma unroll 1
-        for (int j = 0; j < N_TILE / 32; ++j) {  // 32 fp32 channels = one 128-byte staging row
-          uint8_t* stg = smem_stg + buf * kATileBytes;
-          if (etid == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-          uint32_t v0[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 32, v0);
+      for (int j = 0; j < kChunks; ++j) {
+        uint32_t v[32];
+        const float* sc = smem_scale + c0 + j * 64 + half * 32;
+        const float* bi = smem_bias + c0 + j * 64 + half * 32;
+        if constexpr (OUT_F32) {
+          // fp32 output: the two column halves fill one 128-row x 32-float staging buffer each (both buffers per group)
+          if (etid == 0) tma_store_wait_read<0>();
+          named_bar_sync(1, 256);
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64 + half * 32, v);
           tmem_ld_wait();
-          const float* sc = smem_scale + c0 + j * 32;
-          const float* bi = smem_bias + c0 + j * 32;
-          uint8_t* my_row = stg + row * 128;
+          uint8_t* my_row = smem_stg + half * kATileBytes + row * 128;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             uint4 o;
-            o.x = __float_as_uint(fmaf(__uint_as_float(v0[q * 4 + 0]), sc[q * 4 + 0], bi[q * 4 + 0]));
-            o.y = __float_as_uint(fmaf(__uint_as_float(v0[q * 4 + 1]), sc[q * 4 + 1], bi[q * 4 + 1]));
-            o.z = __float_as_uint(fmaf(__uint_as_float(v0[q * 4 + 2]), sc[q * 4 + 2], bi[q * 4 + 2]));
-            o.w = __float_as_uint(fmaf(__uint_as_float(v0[q * 4 + 3]), sc[q * 4 + 3], bi[q * 4 + 3]));
+            o.x = __float_as_uint(fmaf(__uint_as_float(v[q * 4 + 0]), sc[q * 4 + 0], bi[q * 4 + 0]));
+            o.y = __float_as_uint(fmaf(__uint_as_float(v[q * 4 + 1]), sc[q * 4 + 1], bi[q * 4 + 1]));
+            o.z = __float_as_uint(fmaf(__uint_as_float(v[q * 4 + 2]), sc[q * 4 + 2], bi[q * 4 + 2]));
+            o.w = __float_as_uint(fmaf(__uint_as_float(v[q * 4 + 3]), sc[q * 4 + 3], bi[q * 4 + 3]));
             *reinterpret_cast<uint4*>(my_row + ((q ^ (row & 7)) << 4)) = o;
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, 256);
           if (etid == 0) {
-            tma_store_5d(&tmOut, stg, p.out_c_base + c0 + j * 32, w0, p.out_ph, h0, n0);
+            tma_store_5d(&tmOut, smem_stg, p.out_c_base + c0 + j * 64, w0, p.out_ph, h0, n0);
+            tma_store_5d(&tmOut, smem_stg + kATileBytes, p.out_c_base + c0 + j * 64 + 32, w0, p.out_ph, h0, n0);
+            tma_store_commit();
+          }
+        } else {
+          uint8_t* stg = smem_stg + buf * kATileBytes;
+          // staging buffer `buf` was last used two chunks ago: its TMA store must have finished reading smem
+          if (etid == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 256);
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64 + half * 32, v);
+          tmem_ld_wait();
+          if (has_res) mbar_wait(&res_full[rb], rph);
+          const uint8_t* res_row = smem_res + rb * kATileBytes + row * 128;
+          uint8_t* my_row = stg + row * 128;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {  // 4 x 16-byte chunks = this thread's 32 channels
+            float f[8];
+            const float4 s0 = *reinterpret_cast<const float4*>(sc + qq * 8);
+            const float4 s1 = *reinterpret_cast<const float4*>(sc + qq * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(bi + qq * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bi + qq * 8 + 4);
+            const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float biv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[qq * 8 + e]), scv[e], biv[e]);
+            const int chunk16 = ((half * 4 + qq) ^ (row & 7)) << 4;
+            if (has_res) {
+              const uint4 r = *reinterpret_cast<const uint4*>(res_row + chunk16);
+              float2 t;
+              t = unpack2<BF16>(r.x); f[0] += t.x; f[1] += t.y;
+              t = unpack2<BF16>(r.y); f[2] += t.x; f[3] += t.y;
+              t = unpack2<BF16>(r.z); f[4] += t.x; f[5] += t.y;
+              t = unpack2<BF16>(r.w); f[6] += t.x; f[7] += t.y;
+            }
+            if (do_clip) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], 0.0f), p.clip_hi);
+            }
+            uint4 o;
+            o.x = pack2<BF16>(f[0], f[1]);
+            o.y = pack2<BF16>(f[2], f[3]);
+            o.z = pack2<BF16>(f[4], f[5]);
+            o.w = pack2<BF16>(f[6], f[7]);
+            *reinterpret_cast<uint4*>(my_row + chunk16) = o;
+          }
+          fence_proxy_async_smem();
+          if (has_res) {  // residual buffer consumed: hand it back to the prefetcher
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&res_empty[rb]);
+            if (++rb == 2) {
+              rb = 0;
+              rph ^= 1;
+            }
+          }
+          named_bar_sync(1, 256);
+          if (etid == 0) {
+            tma_store_5d(&tmOut, stg, p.out_c_base + c0 + j * 64, w0, p.out_ph, h0, n0);
             tma_store_commit();
           }
           buf ^= 1;
         }
-      } else {
-#pragma unroll 1
-      for (int j = 0; j < kChunks; ++j) {
-        uint8_t* stg = smem_stg + buf * kATileBytes;
-        // staging buffer `buf` was last used two chunks ago: its TMA store must have finished reading smem
-        if (etid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        if (has_res) {
-          if (etid == 0) {
-            mbar_arrive_expect_tx(&res_bar[buf], kATileBytes);
-            tma_load_5d(stg, &tmRes, &res_bar[buf], p.out_c_base + c0 + j * 64, w0, p.out_ph, h0, n0);
-          }
-        }
-        uint32_t v0[32], v1[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64;
-        tmem_ld_32x32(taddr, v0);
-        tmem_ld_32x32(taddr + 32, v1);
-        tmem_ld_wait();
-        if (has_res) {
-          mbar_wait(&res_bar[buf], res_phase[buf]);
-          res_phase[buf] ^= 1;
-        }
-        const float* sc = smem_scale + c0 + j * 64;
-        const float* bi = smem_bias + c0 + j * 64;
-        uint8_t* my_row = stg + row * 128;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {  // 8 x 16-byte chunks = 64 channels
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = q * 8 + e;
-            const float a = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
-            f[e] = fmaf(a, sc[c], bi[c]);
-          }
-          uint4* slot = reinterpret_cast<uint4*>(my_row + ((q ^ (row & 7)) << 4));
-          if (has_res) {
-            const uint4 r = *slot;
-            float2 t;
-            t = unpack2<BF16>(r.x); f[0] += t.x; f[1] += t.y;
-            t = unpack2<BF16>(r.y); f[2] += t.x; f[3] += t.y;
-            t = unpack2<BF16>(r.z); f[4] += t.x; f[5] += t.y;
-            t = unpack2<BF16>(r.w); f[6] += t.x; f[7] += t.y;
-          }
-          if (do_clip) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], 0.0f), p.clip_hi);
-          }
-          uint4 o;
-          o.x = pack2<BF16>(f[0], f[1]);
-          o.y = pack2<BF16>(f[2], f[3]);
-          o.z = pack2<BF16>(f[4], f[5]);
-          o.w = pack2<BF16>(f[6], f[7]);
-          *slot = o;
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (etid == 0) {
-          tma_store_5d(&tmOut, stg, p.out_c_base + c0 + j * 64, w0, p.out_ph, h0, n0);
-          tma_store_commit();
-        }
-        buf ^= 1;
-      }
       }
       // accumulator fully read: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) {
+      if (++acc == kAcc) {
         acc = 0;
         acc_phase ^= 1;
       }

@@ -47,6 +47,22 @@ int fail(int code, const char* fmt, ...) {
       return fail(DSK_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+// Launch with the programmatic-stream-serialization attribute (PDL). Only for kernels that call pdl_wait().
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -161,6 +177,7 @@ struct dsk_handle_s {
   float* zeros = nullptr;  // [512] = 0
   float loss_scale = 0.f;  // 0 = automatic
   std::vector<dsk_train_ctx_s*> ctx_pool;
+  long long* trace = nullptr;  // debug: device buffer [3][512] for conv3x3_halo_kernel clock stamps
   // optional per-launch timing (dsk_set_profiling): events recorded around every kernel of a forward
   bool profiling = false;
   std::vector<cudaEvent_t> events;
@@ -218,8 +235,7 @@ int launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dsk::ConvSmem<N_TILE>::kTotal));
     attr_set = true;
   }
-  kern<<<L.grid, 256, dsk::ConvSmem<N_TILE>::kTotal, s>>>(L.tmA, L.tmB, L.tmOut, L.tmRes, L.p);
-  KERNEL_CHECK();
+  CUDA_TRY(launch_pdl(kern, dim3(L.grid), dim3(dsk::kConvThreads), dsk::ConvSmem<N_TILE>::kTotal, s, L.tmA, L.tmB, L.tmOut, L.tmRes, L.p));
   return DSK_OK;
 }
 
@@ -309,12 +325,18 @@ int build_conv_core(const dsk_handle_s* h, ConvLaunch* L, const View5& a, const 
   p.tiles_h = (Hgrid + p.hb - 1) / p.hb;
   p.tiles_n = (B + p.nb - 1) / p.nb;
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-  // N tile: the largest of {256,128,64} dividing n_out that still gives every SM a tile; else the smallest.
+  // N tile: the kernel is bound by TMA request rate (two boxes per K-step whatever N is), so a tile costs the same
+  // for every N: minimise the number of waves over the SMs; ties go to the smaller tile (more SMs busy).
   int n_tile = 64;
-  for (int cand : {256, 128, 64}) {
+  long best_waves = -1;
+  for (int cand : {64, 128, 256}) {
     if (n_out % cand) continue;
-    n_tile = cand;
-    if (static_cast<long>(tiles_m) * (n_out / cand) >= h->num_sms) break;
+    const long tiles = static_cast<long>(tiles_m) * (n_out / cand);
+    const long waves = (tiles + h->num_sms - 1) / h->num_sms;
+    if (best_waves < 0 || waves < best_waves) {
+      best_waves = waves;
+      n_tile = cand;
+    }
   }
   L->n_tile = n_tile;
   p.tiles_c = n_out / n_tile;
@@ -545,6 +567,9 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   p.scale = scale;
   p.bias = bias;
   p.b_resident = (C == 64) ? 1 : 0;   // 9 taps x 64 x 64 x 2 B = 72 KB stay in shared memory
+  p.trace = h->trace;
+  p.pitch_magic = static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(W + 1)) + 1u;
+  p.img_magic = static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(H + 1)) + 1u;
   const int num_tiles = p.tiles_m * p.tiles_c;
   L->grid = num_tiles < h->num_sms ? num_tiles : h->num_sms;
   const uint64_t npos = static_cast<uint64_t>(padded_positions(N, H, W));
@@ -572,8 +597,7 @@ int launch_halo_t(const HaloLaunch& L, cudaStream_t s) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dsk::HaloSmem<N_TILE>::kTotal));
     attr_set = true;
   }
-  kern<<<L.grid, 256, dsk::HaloSmem<N_TILE>::kTotal, s>>>(L.tmIn, L.tmW, L.tmOut, L.tmRes, L.p);
-  KERNEL_CHECK();
+  CUDA_TRY(launch_pdl(kern, dim3(L.grid), dim3(dsk::kHaloThreads), dsk::HaloSmem<N_TILE>::kTotal, s, L.tmIn, L.tmW, L.tmOut, L.tmRes, L.p));
   return DSK_OK;
 }
 
@@ -819,10 +843,11 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
     const int hout = T / 2;
     const int blocks = B * ((hout + 7) / 8);
     if (h->bf16)
-      dsk::conv1_kernel<true><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->scale[0], h->bias[0], (uint16_t*)pl->act[0], T, 1, 20.0f, 1);
+      CUDA_TRY(launch_pdl(dsk::conv1_kernel<true, false>, dim3(blocks), dim3(256), 0, s, x, (const float*)h->conv1_w,
+                          (const float*)h->scale[0], (const float*)h->bias[0], pl->act[0], T, 1, 20.0f, 1));
     else
-      dsk::conv1_kernel<false><<<blocks, 256, 0, s>>>(x, h->conv1_w, h->scale[0], h->bias[0], (uint16_t*)pl->act[0], T, 1, 20.0f, 1);
-    KERNEL_CHECK();
+      CUDA_TRY(launch_pdl(dsk::conv1_kernel<false, false>, dim3(blocks), dim3(256), 0, s, x, (const float*)h->conv1_w,
+                          (const float*)h->scale[0], (const float*)h->bias[0], pl->act[0], T, 1, 20.0f, 1));
     mark();
   }
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
@@ -834,23 +859,24 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
   {
     const int H4 = T / 16, WC = 4 * 512;
     if (h->bf16)
-      dsk::pool_time_kernel<true><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC, 512, 1);
+      CUDA_TRY(launch_pdl(dsk::pool_time_kernel<true>, dim3(B, WC / 512), dim3(256), 0, s, (const uint16_t*)pl->act[11],
+                          pl->pooled, H4, WC, 512, 1));
     else
-      dsk::pool_time_kernel<false><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)pl->act[11], pl->pooled, H4, WC, 512, 1);
-    KERNEL_CHECK();
+      CUDA_TRY(launch_pdl(dsk::pool_time_kernel<false>, dim3(B, WC / 512), dim3(256), 0, s, (const uint16_t*)pl->act[11],
+                          pl->pooled, H4, WC, 512, 1));
     mark();
     static bool fc_attr = false;
-    const int fc_smem = 8 * 2048 * 4;
+    const int fc_smem = dsk::kFcUtt * 2048 * 4;
     if (!fc_attr) {
       CUDA_TRY(cudaFuncSetAttribute(dsk::fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem));
       fc_attr = true;
     }
-    dim3 g((B + 7) / 8, h->emb / 8);
-    dsk::fc_kernel<<<g, 256, fc_smem, s>>>(pl->pooled, h->fc_wq, h->fc_b, pl->fc_out, B, 2048, h->emb);
-    KERNEL_CHECK();
+    dim3 g((B + dsk::kFcUtt - 1) / dsk::kFcUtt, h->emb / 16);
+    CUDA_TRY(launch_pdl(dsk::fc_kernel, g, dim3(256), fc_smem, s, (const float*)pl->pooled, (const float*)h->fc_wq, h->fc_b,
+                        pl->fc_out, B, 2048, h->emb));
     mark();
-    dsk::l2norm_kernel<<<B, 128, 0, s>>>(pl->fc_out, emb, nullptr, h->emb, 10.0f);
-    KERNEL_CHECK();
+    CUDA_TRY(launch_pdl(dsk::l2norm_kernel, dim3(B), dim3(128), 0, s, (const float*)pl->fc_out, emb, (float*)nullptr, h->emb,
+                        10.0f));
     mark();
   }
   return DSK_OK;
@@ -1040,9 +1066,9 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
     if (bf) dsk::pool_time_kernel<true><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC, 512, 0);
     else dsk::pool_time_kernel<false><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC, 512, 0);
     KERNEL_CHECK();
-    const int fc_smem = 8 * 2048 * 4;
+    const int fc_smem = dsk::kFcUtt * 2048 * 4;
     CUDA_TRY(cudaFuncSetAttribute(dsk::fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem));
-    dim3 g((B + 7) / 8, h->emb / 8);
+    dim3 g((B + dsk::kFcUtt - 1) / dsk::kFcUtt, h->emb / 16);
     dsk::fc_kernel<<<g, 256, fc_smem, s>>>(c->pooled, h->fc_wq, h->fc_b, c->fc_out, B, 2048, h->emb);
     KERNEL_CHECK();
     dsk::l2norm_kernel<<<B, 128, 0, s>>>(c->fc_out, emb, c->inv_norm, h->emb, 10.0f);
@@ -1292,6 +1318,12 @@ int32_t dsk_conv3x3_padded(dsk_handle h, const void* in, const void* w_packed, c
 }
 
 int64_t dsk_padded_positions(int32_t N, int32_t H, int32_t W) { return padded_positions(N, H, W); }
+
+int32_t dsk_debug_set_trace(dsk_handle h, void* device_buffer) {
+  if (!h) return fail(DSK_ERR_INVALID, "null handle");
+  h->trace = static_cast<long long*>(device_buffer);
+  return DSK_OK;
+}
 
 int32_t dsk_conv2d_nhwc(dsk_handle h, const void* in, const void* w_packed, const float* scale, const float* bias,
                         const void* res, void* out, int32_t B, int32_t Hin, int32_t Win, int32_t cin, int32_t cout,

@@ -14,6 +14,31 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp.  Issue code for TMA / tcgen05 must sit under this predicate (not under
+// `lane == 0`): ptxas then knows a single thread executes it and keeps descriptors in uniform registers instead of
+// wrapping every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST waterfall loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  uint32_t laneid = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 %%rx;\n\t"
+      ".reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t"
+      "}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFF));
+  return pred != 0;
+}
+
+// Programmatic dependent launch: every kernel of the forward chain lets its successor start launching at once and
+// waits for its predecessor's memory only right before it first touches activations, so launch latency and the
+// prologue (TMEM allocation, barrier init, scale/bias fetch) overlap the predecessor's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

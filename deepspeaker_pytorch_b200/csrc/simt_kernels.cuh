@@ -65,6 +65,8 @@ conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]
   constexpr int WIN = 64, WOUT = 32, ROWS = 8, PATCH_ROWS = 2 * ROWS + 3, PATCH_W = WIN + 4;
   __shared__ float patch[PATCH_ROWS][PATCH_W];
   __shared__ float wsm[64 * 25];
+  pdl_launch_dependents();
+  pdl_wait();  // the output buffer may still be read by the previous forward's kernels
   const int hout = T / 2;
   const int tiles_h = (hout + ROWS - 1) / ROWS;
   const int n = blockIdx.x / tiles_h;
@@ -127,6 +129,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 pool_time_kernel(const uint16_t* __restrict__ act, float* __restrict__ pooled, int H, int WC, int C, int padded) {
   // grid (B, WC/512): thread = 2 adjacent channels (one 32-bit load per time step), loads independent in h
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int i = blockIdx.y * 256 + threadIdx.x;  // index of the channel pair
   if (i >= WC / 2) return;
@@ -170,65 +174,69 @@ __global__ void pack_fc_weight_kernel(const float* __restrict__ w /*[E][C*4+w]*/
   }
 }
 
-// y[b][e] = sum_k pooled[b][k] * wq[e][k] + bias[e].  grid (ceil(B/8), E/8), block 256 = 8 warps.
-// Warp = one output feature e for 8 utterances: the 8 KB weight row is read once, coalesced (512 B per
-// instruction, 4 independent loads in flight); the 8 pooled vectors sit in shared memory.
+// y[b][e] = sum_k pooled[b][k] * wq[e][k] + bias[e].  grid (ceil(B/16), E/16), block 256 = 8 warps.
+// Block = 16 utterances x 16 output features: the 16 pooled vectors (128 KB fp32) sit in shared memory, every warp
+// owns two features whose 8 KB weight rows are streamed once, coalesced, two loads deep; lane l covers the float4
+// columns l, l+32, ... .  Traffic: weights read B/16 times, pooled vectors E/16 times (4x less than an 8x8 split).
+constexpr int kFcUtt = 16;
 __global__ void __launch_bounds__(256)
 fc_kernel(const float* __restrict__ pooled, const float* __restrict__ wq, const float* __restrict__ bias,
           float* __restrict__ y, int B, int K, int E) {
-  constexpr int UT = 8;
-  extern __shared__ float sp[];  // [UT][K]
-  const int b0 = blockIdx.x * UT;
+  extern __shared__ float sp[];  // [kFcUtt][K]
+  const int b0 = blockIdx.x * kFcUtt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int e = blockIdx.y * 8 + warp;
-  const float4* wr = reinterpret_cast<const float4*>(wq + static_cast<long>(e) * K);
+  const int e0 = blockIdx.y * 16 + warp * 2;
+  const float4* w0 = reinterpret_cast<const float4*>(wq + static_cast<long>(e0) * K);
+  const float4* w1 = reinterpret_cast<const float4*>(wq + static_cast<long>(e0 + 1) * K);
   const int n4 = K / 4;
-  // issue the first weight loads before the shared-memory fill so their latency overlaps it
-  float4 wv[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) wv[j] = wr[j * 32 + lane];
-  for (int i = threadIdx.x; i < UT * n4; i += blockDim.x) {
+  pdl_launch_dependents();
+  float4 a0 = w0[lane], a1 = w1[lane];  // parameters: safe before the dependency wait
+  pdl_wait();
+  for (int i = threadIdx.x; i < kFcUtt * n4; i += blockDim.x) {
     const int u = i / n4;
     reinterpret_cast<float4*>(sp)[i] = (b0 + u < B)
         ? reinterpret_cast<const float4*>(pooled + static_cast<long>(b0 + u) * K)[i - u * n4]
         : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  float acc[UT];
+  float acc0[kFcUtt], acc1[kFcUtt];
 #pragma unroll
-  for (int u = 0; u < UT; ++u) acc[u] = 0.f;
-  for (int i0 = 0; i0 < n4; i0 += 128) {
-    float4 nx[4];
-    const bool more = i0 + 128 < n4;
-    if (more) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) nx[j] = wr[i0 + 128 + j * 32 + lane];
+  for (int u = 0; u < kFcUtt; ++u) acc0[u] = acc1[u] = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    float4 n0 = a0, n1 = a1;
+    if (i + 32 < n4) {
+      n0 = w0[i + 32];
+      n1 = w1[i + 32];
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = i0 + j * 32 + lane;
-#pragma unroll
-      for (int u = 0; u < UT; ++u) {
-        const float4 pv = reinterpret_cast<const float4*>(sp + u * K)[i];
-        acc[u] = fmaf(wv[j].x, pv.x, acc[u]);
-        acc[u] = fmaf(wv[j].y, pv.y, acc[u]);
-        acc[u] = fmaf(wv[j].z, pv.z, acc[u]);
-        acc[u] = fmaf(wv[j].w, pv.w, acc[u]);
-      }
+    for (int u = 0; u < kFcUtt; ++u) {
+      const float4 pv = reinterpret_cast<const float4*>(sp + u * K)[i];
+      acc0[u] = fmaf(a0.x, pv.x, acc0[u]);
+      acc0[u] = fmaf(a0.y, pv.y, acc0[u]);
+      acc0[u] = fmaf(a0.z, pv.z, acc0[u]);
+      acc0[u] = fmaf(a0.w, pv.w, acc0[u]);
+      acc1[u] = fmaf(a1.x, pv.x, acc1[u]);
+      acc1[u] = fmaf(a1.y, pv.y, acc1[u]);
+      acc1[u] = fmaf(a1.z, pv.z, acc1[u]);
+      acc1[u] = fmaf(a1.w, pv.w, acc1[u]);
     }
-    if (more) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wv[j] = nx[j];
-    }
+    a0 = n0;
+    a1 = n1;
   }
 #pragma unroll
-  for (int u = 0; u < UT; ++u)
-    for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+  for (int u = 0; u < kFcUtt; ++u)
+    for (int o = 16; o > 0; o >>= 1) {
+      acc0[u] += __shfl_xor_sync(0xffffffffu, acc0[u], o);
+      acc1[u] += __shfl_xor_sync(0xffffffffu, acc1[u], o);
+    }
   if (lane == 0) {
-    const float bb = bias[e];
+    const float bb0 = bias[e0], bb1 = bias[e0 + 1];
 #pragma unroll
-    for (int u = 0; u < UT; ++u)
-      if (b0 + u < B) y[static_cast<long>(b0 + u) * E + e] = acc[u] + bb;
+    for (int u = 0; u < kFcUtt; ++u)
+      if (b0 + u < B) {
+        y[static_cast<long>(b0 + u) * E + e0] = acc0[u] + bb0;
+        y[static_cast<long>(b0 + u) * E + e0 + 1] = acc1[u] + bb1;
+      }
   }
 }
 
@@ -237,6 +245,8 @@ fc_kernel(const float* __restrict__ pooled, const float* __restrict__ wq, const 
 __global__ void l2norm_kernel(const float* __restrict__ y, float* __restrict__ out, float* __restrict__ inv_norm,
                               int E, float alpha) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const float* yr = y + static_cast<long>(b) * E;
   float s = 0.f;

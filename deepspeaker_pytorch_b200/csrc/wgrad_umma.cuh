@@ -117,21 +117,22 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int tu, co0, ci0, kb, ke;
-        decode(item, tu, co0, ci0, kb, ke);
-        for (int k = kb; k < ke; ++k) {
-          const int cw = k % p.chunks_w;
-          const int r = k / p.chunks_w;
-          const int chh = r % p.chunks_h;
-          const int cn = r / p.chunks_h;
-          const int w0 = cw * p.wt, h0 = chh * p.hb, n0 = cn * p.nb;
-          uint8_t* sa = smem + stage * S::kStageBytes;
-          uint8_t* sb = sa + 2 * kAtomBytes;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // TMA producer: warp-converged loop, one elected lane issues
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int tu, co0, ci0, kb, ke;
+      decode(item, tu, co0, ci0, kb, ke);
+      for (int k = kb; k < ke; ++k) {
+        const int cw = k % p.chunks_w;
+        const int r = k / p.chunks_w;
+        const int chh = r % p.chunks_h;
+        const int cn = r / p.chunks_h;
+        const int w0 = cw * p.wt, h0 = chh * p.hb, n0 = cn * p.nb;
+        uint8_t* sa = smem + stage * S::kStageBytes;
+        uint8_t* sb = sa + 2 * kAtomBytes;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
           if (!p.swapped) {
             tma_load_5d(sa, &tmG, &full_bar[stage], co0, w0, 0, h0, n0);
@@ -147,47 +148,52 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                         h0 + p.tap_dh[t1], n0);
             tma_load_5d(sb, &tmG, &full_bar[stage], 0, w0, 0, h0, n0);
           }
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // fp32 accumulate, both operands MN-major (bits 15 and 16)
-      constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE, BF16) | (1u << 15) | (1u << 16);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int tu, co0, ci0, kb, ke;
-        decode(item, tu, co0, ci0, kb, ke);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // MMA issuer: fp32 accumulate, both operands MN-major (bits 15 and 16)
+    constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE, BF16) | (1u << 15) | (1u << 16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int tu, co0, ci0, kb, ke;
+      decode(item, tu, co0, ci0, kb, ke);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * N_TILE;
+      for (int k = kb; k < ke; ++k) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_TILE;
-        for (int k = kb; k < ke; ++k) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
-          const uint32_t sb = sa + 2 * kAtomBytes;
+        if (elect_one_sync()) {
+          const uint64_t da = umma_desc_mn_sw128(smem_u32(smem + stage * S::kStageBytes));
+          const uint64_t db = umma_desc_mn_sw128(smem_u32(smem + stage * S::kStageBytes + 2 * kAtomBytes));
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)  // 128 pixels = 8 x K16; one K16 step = 16 rows x 128 B
-            umma_f16(d_tmem, umma_desc_mn_sw128(sa + kk * 2048), umma_desc_mn_sw128(sb + kk * 2048), idesc,
-                     (k > kb || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk)  // 128 pixels = 8 x K16; one K16 step = 16 rows x 128 B = +128 in the addr field
+            umma_f16(d_tmem, da + 128 * kk, db + 128 * kk, idesc, (k > kb || kk > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (k == ke - 1) umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&tmem_full[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (ke <= kb) {  // empty K range (split rounding): still hand an (ignored) accumulator to the epilogue
+        if (elect_one_sync()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else if (warp >= 4) {

@@ -144,6 +144,9 @@ int32_t dsk_conv3x3_padded(dsk_handle h, const void* in, const void* w_packed, c
                            const void* res, void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t flags,
                            float clip_hi, void* stream);
 int64_t dsk_padded_positions(int32_t N, int32_t H, int32_t W);
+/* Debug: device buffer of 3*512 int64 that dsk_conv3x3_padded fills with clock64 stamps of CTA 0
+ * (producer / MMA / epilogue roles); NULL switches tracing off. */
+int32_t dsk_debug_set_trace(dsk_handle h, void* device_buffer);
 int32_t dsk_pack_conv_weight(dsk_handle h, const float* w_oihw, void* w_packed, int32_t cout, int32_t cin,
                              int32_t ksize, void* stream);
 /* fp32 NCHW <-> 16-bit NHWC converters (test helpers; also used at the boundary for C>1 inputs) */
