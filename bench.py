@@ -25,6 +25,17 @@ CONV_TC_FLOP_PER_EMB = 2296381440    # the 11 tensor-core convs: 8 x 3x3 (94,371
 L2_BYTES = 126 * 1024 * 1024
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Print the single JSON result line on the real stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -190,7 +201,7 @@ def run_reference(args, rank, world):
                                    f"model.py:185-218 on torch CPU fp32 kernels)"},
         "e2e": {"value": val, "unit": "emb/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_train(args, rank, world, local_rank):
@@ -282,7 +293,7 @@ def run_train(args, rank, world, local_rank):
             "tflops_whole_step": 3 * B * 6911819776 / (ms / K * 1e-3) / 1e12,
             "last_loss": float(loss.item()),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -305,6 +316,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there)
+    # are routed to stderr until the result is printed
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -446,7 +463,7 @@ def main():
     }
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

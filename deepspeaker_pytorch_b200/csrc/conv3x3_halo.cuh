@@ -17,12 +17,38 @@
 
 namespace dsk {
 
+// The same kernel runs the 5x5 stride-2 stage-entry convs (model.py:98,102,106): their input is stored PARITY-PLANAR
+// (four planes (h&1, w&1), each a zero-padded grid at the OUTPUT resolution), so that every tap (r, s) reads plane
+// (r&1, s&1) at a fixed shift ((r-2)>>1, (s-2)>>1) of the output position: one halo box per (64-channel chunk, plane)
+// serves all taps of that plane.  The K loop is table driven: a sequence of weight BOXES (<= 3 taps each, packed
+// consecutively in plane-major tap order), each tap with its own row shift into the current plane's halo tile.
+constexpr int kHaloMaxBoxes = 12;
+constexpr int kHaloMaxStages = 4;
+
 struct HaloParams {
-  int W, H, N;            // image geometry (real pixels)
+  int W, H, N;            // OUTPUT image geometry (real pixels); tiles run over its padded position space
   int q_begin;            // first position of tile 0 (= W+1: first real row)
   int tiles_m, tiles_c;   // 128-position tiles, N_TILE channel tiles
-  int chunks;             // C / 64
+  int chunks;             // Cin / 64
   int cout;
+  // shared-memory carve (runtime): ring depths and buffer counts chosen by the host per layer
+  int a_stage_bytes;      // halo tile rows * 128 rounded up to 1024
+  int a_stages, b_stages; // <= kHaloMaxStages
+  int stg_bufs, res_bufs; // output staging buffers (1 or 2), residual prefetch buffers (0, 1 or 2)
+  // K-loop table (per 64-channel chunk)
+  int nboxes;
+  int plane_positions;                     // positions per input plane (parity-planar input), 0 for a single plane
+  int8_t box_plane[kHaloMaxBoxes];         // input plane of the box's taps
+  int8_t box_first[kHaloMaxBoxes];         // first box of its plane group: load the plane's halo tile
+  int8_t box_last[kHaloMaxBoxes];          // last box of its plane group: release the halo tile
+  int8_t box_ntaps[kHaloMaxBoxes];
+  int16_t box_wtap[kHaloMaxBoxes];         // first packed tap index of the box
+  int16_t tap_shift[kHaloMaxBoxes][3];     // halo-tile row offset of each tap
+  // output: standard padded layout (TMA store) or parity-planar (direct stores; feeds a stride-2 conv)
+  int out_planar;
+  uint16_t* out_ptr;                       // planar destination base
+  int out_plane_positions;                 // positions per output plane
+  int out_C;
   int flags;              // CONV_RESIDUAL | CONV_CLIP
   float clip_hi;
   const float* scale;
@@ -40,16 +66,13 @@ struct HaloParams {
 
 template <int N_TILE>
 struct HaloSmem {
-  static constexpr int kAStageBytes = 25600;                 // 200 rows: 128 + 2W + 4 for W <= 34
-  static constexpr int kBStageBytes = 3 * N_TILE * 128;      // one filter row: 3 taps
-  static constexpr int kAStages = (N_TILE == 64) ? 3 : 2;
-  static constexpr int kBStages = (N_TILE == 64) ? 3 : 2;
-  static constexpr int kStagingBytes = 2 * kATileBytes;
-  static constexpr int kResBytes = 2 * kATileBytes;          // residual tiles prefetched by their own warp
+  static constexpr int kBStageBytes = 3 * N_TILE * 128;      // one weight box: 3 taps
   static constexpr int kScaleBiasBytes = 2 * 512 * 4;
   static constexpr int kAccStages = 4;                       // TMEM accumulators: 4 x N_TILE <= 512 columns
-  static constexpr int kTotal =
-      kAStages * kAStageBytes + kBStages * kBStageBytes + kStagingBytes + kResBytes + kScaleBiasBytes + 256 + 1024;
+  static constexpr int kFixedBytes = kScaleBiasBytes + 512 + 1024;  // scale/bias + barriers + alignment slack
+  static int total(int a_stage_bytes, int a_stages, int b_stages, int stg_bufs, int res_bufs) {
+    return a_stages * a_stage_bytes + b_stages * kBStageBytes + (stg_bufs + res_bufs) * kATileBytes + kFixedBytes;
+  }
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
@@ -77,7 +100,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                     const HaloParams p) {
   using S = HaloSmem<N_TILE>;
-  constexpr int kAStages = S::kAStages, kBStages = S::kBStages;
+  const int kAStages = p.a_stages, kBStages = p.b_stages;
   constexpr int kAcc = S::kAccStages;
   constexpr int kTmemCols = kAcc * N_TILE;
   constexpr int kChunksOut = N_TILE / 64;
@@ -85,17 +108,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + kAStages * S::kAStageBytes;
+  uint8_t* smem_b = smem_a + kAStages * p.a_stage_bytes;
   uint8_t* smem_stg = smem_b + kBStages * S::kBStageBytes;
-  uint8_t* smem_res = smem_stg + S::kStagingBytes;
-  float* smem_scale = reinterpret_cast<float*>(smem_res + S::kResBytes);
+  uint8_t* smem_res = smem_stg + p.stg_bufs * kATileBytes;
+  float* smem_scale = reinterpret_cast<float*>(smem_res + p.res_bufs * kATileBytes);
   float* smem_bias = smem_scale + 512;
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_scale) + S::kScaleBiasBytes);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + kAStages;
-  uint64_t* b_full = a_empty + kAStages;
-  uint64_t* b_empty = b_full + kBStages;
-  uint64_t* tmem_full = b_empty + kBStages;
+  uint64_t* a_empty = a_full + kHaloMaxStages;
+  uint64_t* b_full = a_empty + kHaloMaxStages;
+  uint64_t* b_empty = b_full + kHaloMaxStages;
+  uint64_t* tmem_full = b_empty + kHaloMaxStages;
   uint64_t* tmem_empty = tmem_full + kAcc;
   uint64_t* res_full = tmem_empty + kAcc;
   uint64_t* res_empty = res_full + 2;
@@ -165,24 +188,27 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       int c0, q0;
       decode(tile, c0, q0);
       for (int ch = 0; ch < p.chunks; ++ch) {
-        mbar_wait(&a_empty[as], aph ^ 1);
-        if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&a_full[as], halo_rows * 128);
-          tma_load_2d(smem_a + as * S::kAStageBytes, &tmIn, &a_full[as], ch * 64, q0 - (p.W + 2));
-          DSK_TRACE(0, tcount);
-          ++tcount;
-        }
-        __syncwarp();
-        if (++as == kAStages) {
-          as = 0;
-          aph ^= 1;
-        }
-        if (!p.b_resident || first) {
-          for (int r = 0; r < 3; ++r) {
+        for (int b = 0; b < p.nboxes; ++b) {
+          if (p.box_first[b]) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&a_full[as], halo_rows * 128);
+              tma_load_2d(smem_a + as * p.a_stage_bytes, &tmIn, &a_full[as], ch * 64,
+                          p.box_plane[b] * p.plane_positions + q0 - (p.W + 2));
+              DSK_TRACE(0, tcount);
+              ++tcount;
+            }
+            __syncwarp();
+            if (++as == kAStages) {
+              as = 0;
+              aph ^= 1;
+            }
+          }
+          if (!p.b_resident || first) {
             mbar_wait(&b_empty[bs], bph ^ 1);
             if (elect_one_sync()) {
               mbar_arrive_expect_tx(&b_full[bs], S::kBStageBytes);
-              tma_load_3d(smem_b + bs * S::kBStageBytes, &tmW, &b_full[bs], ch * 64, c0, 3 * r);
+              tma_load_3d(smem_b + bs * S::kBStageBytes, &tmW, &b_full[bs], ch * 64, c0, p.box_wtap[b]);
             }
             __syncwarp();
             if (++bs == kBStages) {
@@ -209,34 +235,35 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       if (lane == 0) DSK_TRACE(1, tcount * 4 + 0);
       const uint32_t d_tmem = tmem_base + acc * N_TILE;
       for (int ch = 0; ch < p.chunks; ++ch) {
-        mbar_wait(&a_full[as], aph);
-        tc_fence_after();
-        if (lane == 0 && ch == 0) DSK_TRACE(1, tcount * 4 + 1);
-        const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a + as * S::kAStageBytes));
-        for (int r = 0; r < 3; ++r) {
-          // resident weights (chunks == 1): filter row r sits in ring slot r for the whole kernel
-          const int slot = p.b_resident ? r : bs;
+        uint64_t da0 = 0;
+        for (int b = 0; b < p.nboxes; ++b) {
+          if (p.box_first[b]) {
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            if (lane == 0 && ch == 0 && b == 0) DSK_TRACE(1, tcount * 4 + 1);
+            da0 = umma_desc_sw128(smem_u32(smem_a + as * p.a_stage_bytes));
+          }
+          // resident weights (one chunk, boxes <= ring size): box b sits in ring slot b for the whole kernel
+          const int slot = p.b_resident ? b : bs;
           if (!p.b_resident || first) {
             mbar_wait(&b_full[slot], bph);
             tc_fence_after();
           }
           if (elect_one_sync()) {
             const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b + slot * S::kBStageBytes));
-            // tap (r, s): A rows shifted by r*(W+1)+s (x 128 B = +8 per row in the addr>>4 field); B tap s is
-            // N_TILE*128 B further; K16 step = +2
-            const uint64_t da_r = da0 + static_cast<uint64_t>(r * pitch) * 8;
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
+            const int nt = p.box_ntaps[b];
+            for (int t = 0; t < nt; ++t) {
+              // tap t of the box: A rows shifted by tap_shift (x 128 B = +8 per row in the addr>>4 field); B tap t is
+              // N_TILE*128 B further; K16 step = +2
+              const uint64_t da = da0 + static_cast<uint64_t>(p.tap_shift[b][t]) * 8;
+              const uint64_t db = db0 + static_cast<uint64_t>(t * (N_TILE * 8));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_f16(d_tmem, da_r + (s * 8 + 2 * k), db0 + (s * (N_TILE * 8) + 2 * k), idesc,
-                         (ch > 0 || r > 0 || s > 0 || k > 0) ? 1u : 0u);
+                umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (ch > 0 || b > 0 || t > 0 || k > 0) ? 1u : 0u);
             }
             if (!p.b_resident) umma_commit(&b_empty[bs]);
-            if (r == 2) {
-              umma_commit(&a_empty[as]);
-              if (ch == p.chunks - 1) umma_commit(&tmem_full[acc]);
-            }
+            if (p.box_last[b]) umma_commit(&a_empty[as]);
+            if (ch == p.chunks - 1 && b == p.nboxes - 1) umma_commit(&tmem_full[acc]);
           }
           __syncwarp();
           if (!p.b_resident) {
@@ -245,10 +272,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
               bph ^= 1;
             }
           }
-        }
-        if (++as == kAStages) {
-          as = 0;
-          aph ^= 1;
+          if (p.box_last[b]) {
+            if (++as == kAStages) {
+              as = 0;
+              aph ^= 1;
+            }
+          }
         }
       }
       if (lane == 0) DSK_TRACE(1, tcount * 4 + 2);
@@ -274,7 +303,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
             tma_load_2d(smem_res + rb * kATileBytes, &tmRes, &res_full[rb], c0 + j * 64, q0);
           }
           __syncwarp();
-          if (++rb == 2) {
+          if (++rb == p.res_bufs) {
             rb = 0;
             rph ^= 1;
           }
@@ -304,6 +333,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       const int cc = q - R * pitch;
       const int img = static_cast<int>(__umulhi(static_cast<unsigned>(R), p.img_magic));
       const bool junk = (cc == 0) || (R - img * (p.H + 1) == 0) || (R >= rows_real_end);
+      // parity-planar destination of this position (only when the consumer is a stride-2 conv): pixel (n, h, w) ->
+      // plane (h&1, w&1), padded position of (n, h>>1, w>>1) on the half-resolution grid
+      uint16_t* planar_row = nullptr;
+      if (p.out_planar && !junk) {
+        const int n = (R - 1 >= 0) ? img : 0;  // R = n*(H+1) + h + 1 with h < H  =>  img == n for real rows
+        const int hh = R - 1 - n * (p.H + 1), ww = cc - 1;
+        const int H2 = p.H >> 1, W2 = p.W >> 1;
+        const long q2 = static_cast<long>(n * (H2 + 1) + (hh >> 1) + 1) * (W2 + 1) + (ww >> 1) + 1;
+        const long plane = (hh & 1) * 2 + (ww & 1);
+        planar_row = p.out_ptr + (plane * p.out_plane_positions + q2) * p.out_C + c0;
+      }
       if (etid == 0) DSK_TRACE(2, ecount * 8 + 0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -311,7 +351,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
 #pragma unroll 1
       for (int j = 0; j < kChunksOut; ++j) {
         uint8_t* stg = smem_stg + buf * kATileBytes;
-        if (etid == 0) tma_store_wait_read<1>();
+        if (etid == 0) {  // the TMA store that last used this staging buffer must have finished reading it
+          if (p.stg_bufs == 2) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
         named_bar_sync(1, 256);
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 2);
         uint32_t v[32];
@@ -355,26 +398,30 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           o.y = pack2<BF16>(f[2], f[3]);
           o.z = pack2<BF16>(f[4], f[5]);
           o.w = pack2<BF16>(f[6], f[7]);
-          if (junk) o = make_uint4(0u, 0u, 0u, 0u);  // pad positions stay zero
-          *slot = o;
+          if (p.out_planar) {
+            if (!junk) *reinterpret_cast<uint4*>(planar_row + (j * 64 + half * 32 + qq * 8)) = o;
+          } else {
+            if (junk) o = make_uint4(0u, 0u, 0u, 0u);  // pad positions stay zero
+            *slot = o;
+          }
         }
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 5);
         fence_proxy_async_smem();
         if (has_res) {  // residual buffer consumed: hand it back to the prefetcher
           __syncwarp();
           if (lane == 0) mbar_arrive(&res_empty[rb]);
-          if (++rb == 2) {
+          if (++rb == p.res_bufs) {
             rb = 0;
             rph ^= 1;
           }
         }
         named_bar_sync(1, 256);
-        if (etid == 0) {
+        if (etid == 0 && !p.out_planar) {
           tma_store_2d(&tmOut, stg, c0 + j * 64, q0);
           tma_store_commit();
         }
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 6);
-        buf ^= 1;
+        if (++buf == p.stg_bufs) buf = 0;
       }
       tc_fence_before();
       __syncwarp();

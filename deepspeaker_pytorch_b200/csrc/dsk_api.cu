@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -128,6 +129,7 @@ struct HaloLaunch {
   dsk::HaloParams p;
   int n_tile = 0;
   int grid = 0;
+  int smem = 0;
 };
 
 struct LayerCfg {
@@ -153,6 +155,8 @@ struct dsk_handle_s {
   // packed parameters
   void* wpk[DSK_NUM_CONV] = {};       // 16-bit [tap][cout][cin]   (conv1: nullptr)
   void* wpk_dgrad[DSK_NUM_CONV] = {}; // 16-bit [tap][cin][cout] for the data gradient (rotated for stride 1)
+  void* wpk_planar[DSK_NUM_CONV] = {}; // 16-bit [plane-major tap][cout][cin] for the halo form of the 5x5 s2 convs
+  int* planar_perm = nullptr;         // device copy of the plane-major tap order
   float* conv1_w = nullptr;           // fp32 [64][25]
   float* scale[DSK_NUM_CONV] = {};    // folded eval BN
   float* bias[DSK_NUM_CONV] = {};
@@ -177,6 +181,7 @@ struct dsk_handle_s {
   float* zeros = nullptr;  // [512] = 0
   float loss_scale = 0.f;  // 0 = automatic
   std::vector<dsk_train_ctx_s*> ctx_pool;
+  bool planar_s2 = false;      // eval forward: run the 5x5 s2 convs in the halo kernel's parity-planar form (DSK_PLANAR_S2=1)
   long long* trace = nullptr;  // debug: device buffer [3][512] for conv3x3_halo_kernel clock stamps
   // optional per-launch timing (dsk_set_profiling): events recorded around every kernel of a forward
   bool profiling = false;
@@ -545,11 +550,27 @@ int build_conv_s2_padded(const dsk_handle_s* h, ConvLaunch* L, const void* in, c
                          20.0f, scale, bias, 0, 0);
 }
 
-// 3x3 s1 p1 conv, C -> C, on the padded layout with halo reuse.
+// Packed tap order of the parity-planar 5x5 s2 conv: plane (ph, pw) major, then r, then s. slot -> original r*5+s.
+void planar_tap_order(int* perm /*[25]*/) {
+  int n = 0;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw)
+      for (int r = ph; r < 5; r += 2)
+        for (int s = pw; s < 5; s += 2) perm[n++] = r * 5 + s;
+}
+
+// Halo-reuse conv on the padded layout (conv3x3_halo.cuh).  ksize 3 (stride 1, C -> C, input = standard padded
+// layout of the same geometry) or ksize 5 (stride 2, input = parity-planar padded layout at the OUTPUT geometry).
+// (N, H, W) is the OUTPUT geometry.  out_planar: write the output parity-planar (it feeds a stride-2 conv).
 int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void* wpk, const float* scale,
-               const float* bias, const void* res, void* out, int N, int H, int W, int C, int flags, float clip_hi) {
-  if (C % 64 || C < 64 || C > 512) return fail(DSK_ERR_INVALID, "halo conv: C must be a multiple of 64 (got %d)", C);
+               const float* bias, const void* res, void* out, int N, int H, int W, int cin, int cout, int ksize,
+               int flags, float clip_hi, int out_planar) {
+  if (cin % 64 || cin < 64 || cout % 64 || cout < 64 || cout > 512)
+    return fail(DSK_ERR_INVALID, "halo conv: channel counts must be multiples of 64 (got %d -> %d)", cin, cout);
+  if (ksize != 3 && ksize != 5) return fail(DSK_ERR_INVALID, "halo conv: ksize must be 3 or 5");
+  if (ksize == 3 && cin != cout) return fail(DSK_ERR_INVALID, "halo conv: the 3x3 form needs cin == cout");
   if (W > 34) return fail(DSK_ERR_INVALID, "halo conv: W must be <= 34 (got %d)", W);
+  if (out_planar && ((H & 1) || (W & 1))) return fail(DSK_ERR_INVALID, "halo conv: planar output needs even H, W");
   const bool bf = h->bf16;
   dsk::HaloParams& p = L->p;
   memset(&p, 0, sizeof(p));
@@ -557,36 +578,112 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   p.q_begin = W + 1;
   const long q_end = static_cast<long>(N) * (H + 1) * (W + 1);   // one past the last real pixel position
   p.tiles_m = static_cast<int>((q_end - p.q_begin + 127) / 128);
-  const int n_tile = C == 64 ? 64 : 128;
+  const int n_tile = cout == 64 ? 64 : 128;
   L->n_tile = n_tile;
-  p.tiles_c = C / n_tile;
-  p.chunks = C / 64;
-  p.cout = C;
+  p.tiles_c = cout / n_tile;
+  p.chunks = cin / 64;
+  p.cout = cout;
   p.flags = flags;
   p.clip_hi = clip_hi;
   p.scale = scale;
   p.bias = bias;
-  p.b_resident = (C == 64) ? 1 : 0;   // 9 taps x 64 x 64 x 2 B = 72 KB stay in shared memory
   p.trace = h->trace;
   p.pitch_magic = static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(W + 1)) + 1u;
   p.img_magic = static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(H + 1)) + 1u;
+  const long npos = padded_positions(N, H, W);
+  int ntaps_total;
+  if (ksize == 3) {
+    ntaps_total = 9;
+    p.nboxes = 3;
+    p.plane_positions = 0;
+    for (int r = 0; r < 3; ++r) {
+      p.box_plane[r] = 0;
+      p.box_first[r] = r == 0;
+      p.box_last[r] = r == 2;
+      p.box_ntaps[r] = 3;
+      p.box_wtap[r] = (int16_t)(3 * r);
+      for (int s2 = 0; s2 < 3; ++s2) p.tap_shift[r][s2] = (int16_t)(r * (W + 1) + s2);
+    }
+  } else {
+    ntaps_total = 25;
+    p.plane_positions = static_cast<int>(npos);
+    int perm[25];
+    planar_tap_order(perm);
+    int slot = 0, nb = 0;
+    for (int pl = 0; pl < 4; ++pl) {
+      const int ph = pl >> 1, pw = pl & 1;
+      const int cnt = (ph ? 2 : 3) * (pw ? 2 : 3);
+      for (int t0 = 0; t0 < cnt; t0 += 3, ++nb) {
+        p.box_plane[nb] = (int8_t)pl;
+        p.box_first[nb] = t0 == 0;
+        p.box_last[nb] = t0 + 3 >= cnt;
+        p.box_ntaps[nb] = (int8_t)(cnt - t0 < 3 ? cnt - t0 : 3);
+        p.box_wtap[nb] = (int16_t)(slot + t0);
+        for (int t = 0; t < p.box_ntaps[nb]; ++t) {
+          const int rs = perm[slot + t0 + t];
+          const int dh = ((rs / 5) - 2) >> 1, dw = ((rs % 5) - 2) >> 1;
+          p.tap_shift[nb][t] = (int16_t)((dh + 1) * (W + 1) + dw + 1);
+        }
+      }
+      slot += cnt;
+    }
+    p.nboxes = nb;  // 3 + 2 + 2 + 2 = 9
+  }
+  // all weight boxes of a CTA fit the B ring and every tile of the CTA uses the same ones: load them once
+  p.b_resident = (p.chunks == 1 && p.tiles_c == 1 && p.nboxes <= 3 && n_tile == 64) ? 1 : 0;
+  p.out_planar = out_planar;
+  if (out_planar) {
+    p.out_ptr = static_cast<uint16_t*>(out);
+    p.out_plane_positions = static_cast<int>(padded_positions(N, H / 2, W / 2));
+    p.out_C = cout;
+  }
+  // shared-memory carve: weight boxes are the latency-critical stream (48 KB each at N_TILE = 128), so they get the
+  // deepest ring that fits in 227 KB; output staging / residual prefetch shrink to one buffer each when needed
+  {
+    const int halo_rows = 128 + 2 * W + 4;
+    p.a_stage_bytes = (halo_rows * 128 + 1023) / 1024 * 1024;
+    const bool has_res = (flags & dsk::CONV_RESIDUAL) != 0;
+    const int b_bytes = 3 * n_tile * 128;
+    const int fixed = n_tile == 64 ? dsk::HaloSmem<64>::kFixedBytes : dsk::HaloSmem<128>::kFixedBytes;
+    const int limit = 227 * 1024;
+    p.a_stages = n_tile == 64 ? 3 : 2;
+    p.stg_bufs = 2;
+    p.res_bufs = has_res ? 2 : 0;
+    auto fit_b = [&]() { return (limit - fixed - p.a_stages * p.a_stage_bytes - (p.stg_bufs + p.res_bufs) * 16384) / b_bytes; };
+    int nb = fit_b();
+    if (nb < 3 && !p.b_resident) {  // trade buffers for a third weight stage
+      if (has_res) p.res_bufs = 1;
+      p.stg_bufs = 1;
+      nb = fit_b();
+      if (nb < 3) p.stg_bufs = 2, p.res_bufs = has_res ? 2 : 0, nb = fit_b();
+    }
+    p.b_stages = nb > dsk::kHaloMaxStages ? dsk::kHaloMaxStages : nb;
+    if (p.b_resident) p.b_stages = 3;
+    if (p.b_stages < 2) return fail(DSK_ERR_INVALID, "halo conv: shared memory does not fit");
+    L->smem = p.a_stages * p.a_stage_bytes + p.b_stages * b_bytes + (p.stg_bufs + p.res_bufs) * 16384 + fixed;
+  }
   const int num_tiles = p.tiles_m * p.tiles_c;
   L->grid = num_tiles < h->num_sms ? num_tiles : h->num_sms;
-  const uint64_t npos = static_cast<uint64_t>(padded_positions(N, H, W));
-  uint64_t dims[2] = {(uint64_t)C, npos};
-  uint64_t str[1] = {2ull * C};
+  const uint64_t in_pos = static_cast<uint64_t>(npos) * (ksize == 5 ? 4 : 1);
+  uint64_t idims[2] = {(uint64_t)cin, in_pos};
+  uint64_t istr[1] = {2ull * cin};
   uint32_t box_in[2] = {64, (uint32_t)(128 + 2 * W + 4)};
-  uint32_t box_out[2] = {64, 128};
-  int rc = make_tmap(&L->tmIn, bf, in, 2, dims, str, box_in);
+  int rc = make_tmap(&L->tmIn, bf, in, 2, idims, istr, box_in);
   if (rc) return rc;
-  uint64_t wd[3] = {(uint64_t)C, (uint64_t)C, 9};
-  uint64_t ws[2] = {2ull * C, 2ull * C * C};
+  uint64_t wd[3] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)ntaps_total};
+  uint64_t ws[2] = {2ull * cin, 2ull * cin * cout};
   uint32_t wb[3] = {64, (uint32_t)n_tile, 3};
   rc = make_tmap(&L->tmW, bf, wpk, 3, wd, ws, wb);
   if (rc) return rc;
-  rc = make_tmap(&L->tmOut, bf, out, 2, dims, str, box_out);
+  // output / residual: standard padded layout of the output geometry (with a planar output the map is unused but
+  // must be valid: point it at the residual or the input)
+  uint64_t odims[2] = {(uint64_t)cout, (uint64_t)npos};
+  uint64_t ostr[1] = {2ull * cout};
+  uint32_t box_out[2] = {64, 128};
+  const void* res_ptr = (flags & dsk::CONV_RESIDUAL) ? res : (out_planar ? in : out);
+  rc = make_tmap(&L->tmRes, bf, res_ptr, 2, odims, ostr, box_out);
   if (rc) return rc;
-  return make_tmap(&L->tmRes, bf, (flags & dsk::CONV_RESIDUAL) ? res : out, 2, dims, str, box_out);
+  return make_tmap(&L->tmOut, bf, out_planar ? res_ptr : out, 2, odims, ostr, box_out);
 }
 
 template <int N_TILE, bool BF16>
@@ -594,10 +691,10 @@ int launch_halo_t(const HaloLaunch& L, cudaStream_t s) {
   auto kern = dsk::conv3x3_halo_kernel<N_TILE, BF16>;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dsk::HaloSmem<N_TILE>::kTotal));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  CUDA_TRY(launch_pdl(kern, dim3(L.grid), dim3(dsk::kHaloThreads), dsk::HaloSmem<N_TILE>::kTotal, s, L.tmIn, L.tmW, L.tmOut, L.tmRes, L.p));
+  CUDA_TRY(launch_pdl(kern, dim3(L.grid), dim3(dsk::kHaloThreads), L.smem, s, L.tmIn, L.tmW, L.tmOut, L.tmRes, L.p));
   return DSK_OK;
 }
 
@@ -642,7 +739,10 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
     int H, W, C;
     act_shape(i, T, H, W, C);
     off[i] = bytes;
-    bytes += ((padded_bytes(B, H, W, C) + 1023) / 1024) * 1024;
+    // optional: a block output that feeds a stride-2 conv (i = 2, 5, 8) stored parity-planar (4 planes at half res)
+    const bool planar = h->planar_s2 && (i % 3 == 2) && i < DSK_NUM_CONV - 1;
+    const size_t b = planar ? 4 * padded_bytes(B, H / 2, W / 2, C) : padded_bytes(B, H, W, C);
+    bytes += ((b + 1023) / 1024) * 1024;
   }
   const size_t act_bytes = bytes;
   const size_t off_pooled = bytes;
@@ -678,15 +778,23 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
     int Hi, Wi, Ci;
     act_shape(i - 1, T, Hi, Wi, Ci);  // input of conv i is activation i-1
     const int k = i % 3;
+    int Ho, Wo, Co;
+    act_shape(i, T, Ho, Wo, Co);
     int rc;
-    if (k == 0) {
+    if (k == 0 && h->planar_s2) {
+      rc = build_halo(h, &pl.halo[i], pl.act[i - 1], h->wpk_planar[i], h->scale[i], h->bias[i], nullptr, pl.act[i], B, Ho, Wo,
+                      c.cin, c.cout, 5, dsk::CONV_CLIP, 20.0f, 0);
+    } else if (k == 0) {
+      // default: the generic tap kernel reads the padded input through its parity view (measured 4 % faster end to end
+      // than the planar form at batch 64: both are bound by operand delivery, and planar stores cost the producer)
       rc = build_conv_s2_padded(h, &pl.conv[i], pl.act[i - 1], h->wpk[i], h->scale[i], h->bias[i], pl.act[i], B, Hi, Wi,
                                 c.cin, c.cout);
     } else {
       const void* res = (k == 2) ? pl.act[i - 2] : nullptr;  // block output adds the block input
       const int flags = dsk::CONV_CLIP | (k == 2 ? dsk::CONV_RESIDUAL : 0);
-      rc = build_halo(h, &pl.halo[i], pl.act[i - 1], h->wpk[i], h->scale[i], h->bias[i], res, pl.act[i], B, Hi, Wi, c.cin,
-                      flags, 20.0f);
+      const int out_planar = (h->planar_s2 && k == 2 && i < DSK_NUM_CONV - 1) ? 1 : 0;
+      rc = build_halo(h, &pl.halo[i], pl.act[i - 1], h->wpk[i], h->scale[i], h->bias[i], res, pl.act[i], B, Ho, Wo, c.cin,
+                      c.cout, 3, flags, 20.0f, out_planar);
     }
     if (rc) return rc;
   }
@@ -719,6 +827,10 @@ int32_t dsk_create(dsk_handle* out, int32_t device, int32_t operand) {
   h->bf16 = operand == DSK_BF16;
   h->num_sms = prop.multiProcessorCount;
   {
+    const char* e = getenv("DSK_PLANAR_S2");
+    h->planar_s2 = e && e[0] == '1';
+  }
+  {
     std::vector<float> one(512, 1.0f);
     if (cudaMalloc(reinterpret_cast<void**>(&h->ones), 512 * 4) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&h->zeros), 512 * 4) != cudaSuccess ||
@@ -738,10 +850,12 @@ int32_t dsk_destroy(dsk_handle h) {
   for (int i = 0; i < DSK_NUM_CONV; ++i) {
     cudaFree(h->wpk[i]);
     cudaFree(h->wpk_dgrad[i]);
+    cudaFree(h->wpk_planar[i]);
     cudaFree(h->scale[i]);
     cudaFree(h->bias[i]);
   }
   cudaFree(h->conv1_w);
+  cudaFree(h->planar_perm);
   cudaFree(h->fc_wq);
   cudaFree(h->ws);
   cudaFree(h->ones);
@@ -801,6 +915,21 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
       dsk::pack_conv_weight_dgrad_kernel<false><<<blocks, 256, 0, s>>>(w->conv_w[i], (uint16_t*)h->wpk_dgrad[i], c.cout, c.cin, taps, c.stride == 1);
     }
     KERNEL_CHECK();
+    if (c.stride == 2) {
+      if (!h->planar_perm) {
+        int perm[25];
+        planar_tap_order(perm);
+        rc = dev_alloc(&h->planar_perm, 25);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpy(h->planar_perm, perm, sizeof(perm), cudaMemcpyHostToDevice));
+      }
+      if (!h->wpk_planar[i]) CUDA_TRY(cudaMalloc(&h->wpk_planar[i], n * 2));
+      if (h->bf16)
+        dsk::pack_conv_weight_perm_kernel<true><<<blocks, 256, 0, s>>>(w->conv_w[i], (uint16_t*)h->wpk_planar[i], c.cout, c.cin, taps, h->planar_perm);
+      else
+        dsk::pack_conv_weight_perm_kernel<false><<<blocks, 256, 0, s>>>(w->conv_w[i], (uint16_t*)h->wpk_planar[i], c.cout, c.cin, taps, h->planar_perm);
+      KERNEL_CHECK();
+    }
   }
   if (!w->fc_w || !w->fc_b) return fail(DSK_ERR_INVALID, "dsk_load_weights: null fc pointer");
   if (!h->fc_wq) {
@@ -851,7 +980,7 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
     mark();
   }
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
-    rc = (i % 3 == 0) ? launch_conv(h, pl->conv[i], s) : launch_halo(h, pl->halo[i], s);
+    rc = (i % 3 == 0 && !h->planar_s2) ? launch_conv(h, pl->conv[i], s) : launch_halo(h, pl->halo[i], s);
     if (rc) return rc;
     mark();
   }
@@ -1306,15 +1435,44 @@ int32_t dsk_bn_act_train_backward(dsk_handle h, const void* gy, const void* y, c
 
 int32_t dsk_conv3x3_padded(dsk_handle h, const void* in, const void* w_packed, const float* scale, const float* bias,
                            const void* res, void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t flags,
-                           float clip_hi, void* stream) {
+                           float clip_hi, int32_t out_planar, void* stream) {
   int rc = check_handle(h);
   if (rc) return rc;
   if (!in || !w_packed || !out) return fail(DSK_ERR_INVALID, "dsk_conv3x3_padded: null pointer");
   if ((flags & dsk::CONV_RESIDUAL) && !res) return fail(DSK_ERR_INVALID, "dsk_conv3x3_padded: residual flag without res");
   HaloLaunch L;
-  rc = build_halo(h, &L, in, w_packed, scale, bias, res, out, N, H, W, C, flags, clip_hi);
+  rc = build_halo(h, &L, in, w_packed, scale, bias, res, out, N, H, W, C, C, 3, flags, clip_hi, out_planar);
   if (rc) return rc;
   return launch_halo(h, L, static_cast<cudaStream_t>(stream));
+}
+
+int32_t dsk_conv5x5s2_planar(dsk_handle h, const void* in_planar, const float* w_oihw, const float* scale,
+                             const float* bias, void* out, int32_t N, int32_t Hout, int32_t Wout, int32_t cin,
+                             int32_t cout, int32_t flags, float clip_hi, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!in_planar || !w_oihw || !out) return fail(DSK_ERR_INVALID, "dsk_conv5x5s2_planar: null pointer");
+  if (flags & dsk::CONV_RESIDUAL) return fail(DSK_ERR_INVALID, "dsk_conv5x5s2_planar: no residual on this path");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long n = static_cast<long>(cout) * cin * 25;
+  void* wpk = nullptr;
+  int* perm_d = nullptr;
+  int perm[25];
+  planar_tap_order(perm);
+  CUDA_TRY(cudaMallocAsync(&wpk, n * 2, s));
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&perm_d), sizeof(perm), s));
+  CUDA_TRY(cudaMemcpyAsync(perm_d, perm, sizeof(perm), cudaMemcpyHostToDevice, s));
+  const int blocks = static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  if (h->bf16) dsk::pack_conv_weight_perm_kernel<true><<<blocks, 256, 0, s>>>(w_oihw, (uint16_t*)wpk, cout, cin, 25, perm_d);
+  else dsk::pack_conv_weight_perm_kernel<false><<<blocks, 256, 0, s>>>(w_oihw, (uint16_t*)wpk, cout, cin, 25, perm_d);
+  KERNEL_CHECK();
+  CUDA_TRY(cudaStreamSynchronize(s));  // perm[] is a stack array
+  HaloLaunch L;
+  rc = build_halo(h, &L, in_planar, wpk, scale, bias, nullptr, out, N, Hout, Wout, cin, cout, 5, flags, clip_hi, 0);
+  if (!rc) rc = launch_halo(h, L, s);
+  CUDA_TRY(cudaFreeAsync(wpk, s));
+  CUDA_TRY(cudaFreeAsync(perm_d, s));
+  return rc;
 }
 
 int64_t dsk_padded_positions(int32_t N, int32_t H, int32_t W) { return padded_positions(N, H, W); }

@@ -22,6 +22,21 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, uint16_t* _
   }
 }
 
+// [slot][cout][cin] with slot -> original tap perm[slot] (plane-major tap order of the halo 5x5 s2 conv).
+template <bool BF16>
+__global__ void pack_conv_weight_perm_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int cout, int cin,
+                                             int taps, const int* __restrict__ perm) {
+  const long total = static_cast<long>(cout) * cin * taps;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ci = i % cin;
+    const long r = i / cin;
+    const int co = r % cout;
+    const int slot = r / cout;
+    out[i] = to16<BF16>(w[(static_cast<long>(co) * cin + ci) * taps + perm[slot]]);
+  }
+}
+
 // Same with cin/cout swapped (the weight of "data-gradient as a convolution"): out[tap'][ci][co] =
 // w[co][ci][rotate ? taps-1-tap' : tap'].  rotate=1 (filter turned by 180 degrees) for stride-1 convs; the
 // stride-2 data-gradient picks its taps by index and keeps the original order.
@@ -72,12 +87,30 @@ conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]
   const int n = blockIdx.x / tiles_h;
   const int h0 = (blockIdx.x % tiles_h) * ROWS;
   const float* xin = x + static_cast<long>(n) * T * WIN;
-  for (int i = threadIdx.x; i < PATCH_ROWS * PATCH_W; i += blockDim.x) {
-    const int pr = i / PATCH_W, pc = i % PATCH_W;
-    const int ih = 2 * h0 - 2 + pr, iw = pc - 2;
-    patch[pr][pc] = (ih >= 0 && ih < T && iw >= 0 && iw < WIN) ? xin[ih * WIN + iw] : 0.0f;
+  {
+    constexpr int NEL = PATCH_ROWS * PATCH_W, NIT = (NEL + 255) / 256;
+    float t[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {  // all loads first (independent), then the stores
+      const int i = threadIdx.x + 256 * j;
+      const int pr = i / PATCH_W, pc = i % PATCH_W;
+      const int ih = 2 * h0 - 2 + pr, iw = pc - 2;
+      t[j] = (i < NEL && ih >= 0 && ih < T && iw >= 0 && iw < WIN) ? xin[ih * WIN + iw] : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      if (i < NEL) patch[i / PATCH_W][i % PATCH_W] = t[j];
+    }
   }
-  for (int i = threadIdx.x; i < 64 * 25; i += blockDim.x) wsm[i] = w[i];
+  {
+    float t[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) t[j] = (threadIdx.x + 256 * j < 64 * 25) ? w[threadIdx.x + 256 * j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (threadIdx.x + 256 * j < 64 * 25) wsm[threadIdx.x + 256 * j] = t[j];
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = lane * 2;
@@ -192,11 +225,19 @@ fc_kernel(const float* __restrict__ pooled, const float* __restrict__ wq, const 
   pdl_launch_dependents();
   float4 a0 = w0[lane], a1 = w1[lane];  // parameters: safe before the dependency wait
   pdl_wait();
-  for (int i = threadIdx.x; i < kFcUtt * n4; i += blockDim.x) {
-    const int u = i / n4;
-    reinterpret_cast<float4*>(sp)[i] = (b0 + u < B)
-        ? reinterpret_cast<const float4*>(pooled + static_cast<long>(b0 + u) * K)[i - u * n4]
-        : make_float4(0.f, 0.f, 0.f, 0.f);
+  // shared-memory fill: warp w copies utterances w and w+8, eight independent 16-byte loads in flight per lane
+  for (int u = warp; u < kFcUtt; u += 8) {
+    const bool ok = b0 + u < B;
+    const float4* src = reinterpret_cast<const float4*>(pooled + static_cast<long>(ok ? b0 + u : 0) * K);
+    float4* dst = reinterpret_cast<float4*>(sp) + u * n4;
+    for (int i0 = lane; i0 < n4; i0 += 256) {
+      float4 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = (ok && i0 + 32 * j < n4) ? src[i0 + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (i0 + 32 * j < n4) dst[i0 + 32 * j] = t[j];
+    }
   }
   __syncthreads();
   float acc0[kFcUtt], acc1[kFcUtt];

@@ -137,12 +137,19 @@ int32_t dsk_bn_act_train_forward(dsk_handle h, const float* raw, const float* ga
 int32_t dsk_bn_act_train_backward(dsk_handle h, const void* gy, const void* y, const float* raw, const float* gamma,
                                   const float* mean, const float* rstd, void* G, void* gres, float* dgamma,
                                   float* dbeta, int64_t M, int32_t C, float inv_scale, void* stream);
-/* The eval forward's 3x3 s1 conv (C -> C) on the zero-padded NHWC layout with halo reuse (csrc/conv3x3_halo.cuh):
- * tensors are [dsk_padded_positions(N,H,W)][C] 16-bit, pixel (n,h,w) at position (n*(H+1)+h+1)*(W+1) + w+1, all
- * other positions zero.  Exported for unit tests.  W <= 34. */
+/* The eval forward's convs on the zero-padded NHWC layout with halo reuse (csrc/conv3x3_halo.cuh), exported for
+ * unit tests.  Standard padded tensor: [dsk_padded_positions(N,H,W)][C] 16-bit, pixel (n,h,w) at position
+ * (n*(H+1)+h+1)*(W+1) + w+1, every other position zero.  Parity-planar tensor of an (N,H,W,C) image (H, W even):
+ * four planes p = (h&1)*2 + (w&1), plane p = standard padded tensor of geometry (N, H/2, W/2) holding pixel
+ * (n, h>>1, w>>1), planes dsk_padded_positions(N,H/2,W/2) positions apart.  W <= 34.
+ * dsk_conv3x3_padded: 3x3 s1 p1, C -> C, standard in; out standard (out_planar = 0) or parity-planar (1).
+ * dsk_conv5x5s2_planar: 5x5 s2 p2, parity-planar input of the (N, 2*Hout, 2*Wout, cin) image -> standard padded out. */
 int32_t dsk_conv3x3_padded(dsk_handle h, const void* in, const void* w_packed, const float* scale, const float* bias,
                            const void* res, void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t flags,
-                           float clip_hi, void* stream);
+                           float clip_hi, int32_t out_planar, void* stream);
+int32_t dsk_conv5x5s2_planar(dsk_handle h, const void* in_planar, const float* w_oihw, const float* scale,
+                             const float* bias, void* out, int32_t N, int32_t Hout, int32_t Wout, int32_t cin,
+                             int32_t cout, int32_t flags, float clip_hi, void* stream);
 int64_t dsk_padded_positions(int32_t N, int32_t H, int32_t W);
 /* Debug: device buffer of 3*512 int64 that dsk_conv3x3_padded fills with clock64 stamps of CTA 0
  * (producer / MMA / epilogue roles); NULL switches tracing off. */

@@ -29,12 +29,12 @@ for name, path in libs.items():
         s = torch.cuda.current_stream().cuda_stream
         for flags in (2, 3):
             for _ in range(3):
-                assert lib.dsk_conv3x3_padded(h, x.data_ptr(), wp.data_ptr(), sc.data_ptr(), bi.data_ptr(), r.data_ptr(), o.data_ptr(), N, H, W, C, flags, 20.0, s) == 0
+                assert lib.dsk_conv3x3_padded(h, x.data_ptr(), wp.data_ptr(), sc.data_ptr(), bi.data_ptr(), r.data_ptr(), o.data_ptr(), N, H, W, C, flags, 20.0, 0, s) == 0
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(20):
-                lib.dsk_conv3x3_padded(h, x.data_ptr(), wp.data_ptr(), sc.data_ptr(), bi.data_ptr(), r.data_ptr(), o.data_ptr(), N, H, W, C, flags, 20.0, s)
+                lib.dsk_conv3x3_padded(h, x.data_ptr(), wp.data_ptr(), sc.data_ptr(), bi.data_ptr(), r.data_ptr(), o.data_ptr(), N, H, W, C, flags, 20.0, 0, s)
             e1.record(); torch.cuda.synchronize()
             out.append(f"{e0.elapsed_time(e1) / 20 * 1e3:6.1f}")
     print(f"{name:5s} us per launch [S1 nores,res | S2 | S3 | S4]: " + " ".join(out), flush=True)

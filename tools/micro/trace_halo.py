@@ -17,7 +17,7 @@ s = torch.cuda.current_stream().cuda_stream
 tr = torch.zeros(3 * 512, dtype=torch.int64, device="cuda")
 for it in range(3):
     if it == 2: L.check(lib.dsk_debug_set_trace(h, tr.data_ptr()))
-    L.check(lib.dsk_conv3x3_padded(h, x.data_ptr(), wp.data_ptr(), sc.data_ptr(), bi.data_ptr(), r.data_ptr(), o.data_ptr(), N, H, W, C, flags, 20.0, s))
+    L.check(lib.dsk_conv3x3_padded(h, x.data_ptr(), wp.data_ptr(), sc.data_ptr(), bi.data_ptr(), r.data_ptr(), o.data_ptr(), N, H, W, C, flags, 20.0, 0, s))
 torch.cuda.synchronize()
 t = tr.cpu().view(3, 512)
 t0 = int(t[t > 0].min())
