@@ -1,39 +1,61 @@
-"""Host-to-host embedding extraction with copy/compute overlap.
+"""Host-to-host (or device-to-device) embedding extraction with copy/compute overlap and two forwards in flight.
 
 The reference's ``test()`` loop (/root/reference/train_triplet.py:337-350) moves every batch to the GPU, runs the
 model and pulls the distances back, all serialised on one stream.  ``EmbeddingPipeline`` keeps the same per-batch
-call (``embed(x_host) -> embeddings on the host``) but runs the H2D copy of batch i+1 and the D2H copy of batch
-i-1 on their own streams while batch i is in the ResCNN kernels (PCIe is full duplex; the copies are ~2.7 MB in,
-128 KB out per 64 utterances).
+call but
+
+* runs the H2D copy of batch i+1 and the D2H copy of batch i-1 on their own streams while batch i is in the ResCNN
+  kernels (PCIe is full duplex; 2.6 MB in, 128 KB out per 64 utterances), and
+* alternates batches between ``lanes`` compute streams, each with its own engine handle and activation workspace:
+  the late ResCNN stages of a 64-utterance batch have only 80-190 tiles for 148 SMs, so a second forward in flight
+  fills the SMs the first one leaves idle.
 """
 from __future__ import annotations
 
 import torch
 
+from . import engine as _engine
+
 
 class EmbeddingPipeline:
-    def __init__(self, model, depth: int = 2):
+    def __init__(self, model, lanes: int = 3, depth: int = 2):
         p = next(model.parameters())
         if not p.is_cuda:
             raise RuntimeError("EmbeddingPipeline needs the model on a CUDA device")
+        if model.training:
+            raise RuntimeError("EmbeddingPipeline is an inference helper: call model.eval() first")
         self.model = model
         self.device = p.device
         self.depth = depth
         self.h2d = torch.cuda.Stream(self.device)
         self.d2h = torch.cuda.Stream(self.device)
-        self.compute = torch.cuda.Stream(self.device)
+        self.lanes = [torch.cuda.Stream(self.device) for _ in range(lanes)]
+        # lane 0 uses the module's own engine, further lanes get private engines (own packed weights + workspace)
+        self.engines = [model._get_engine(self.device)] + [
+            _engine.Engine(model, self.device, model.operand_dtype) for _ in range(lanes - 1)]
         self._slots = {}
         self._i = 0
 
     def _slot(self, shape, k):
         key = (tuple(shape), k)
         if key not in self._slots:
-            self._slots[key] = {
-                "x": torch.empty(shape, device=self.device, dtype=torch.float32),
-                "h2d_done": torch.cuda.Event(), "free": torch.cuda.Event(), "emb_ready": torch.cuda.Event(),
-            }
-            self._slots[key]["free"].record(self.compute)
+            s = {"x": torch.empty(shape, device=self.device, dtype=torch.float32),
+                 "h2d_done": torch.cuda.Event(), "free": torch.cuda.Event(), "emb_ready": torch.cuda.Event()}
+            s["free"].record(torch.cuda.current_stream(self.device))
+            self._slots[key] = s
         return self._slots[key]
+
+    @torch.no_grad()
+    def embed_device(self, x: torch.Tensor) -> torch.Tensor:
+        """Queue one device-resident batch on the next compute lane; returns the (asynchronously produced) embeddings.
+        The caller orders its own streams against ``lane_of(result)`` / ``synchronize()``."""
+        lane = self._i % len(self.lanes)
+        self._i += 1
+        st = self.lanes[lane]
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st):
+            emb = self.engines[lane].forward(x, False)
+        return emb
 
     @torch.no_grad()
     def embed(self, x_host: torch.Tensor, out_host: torch.Tensor) -> torch.cuda.Event:
@@ -41,17 +63,19 @@ class EmbeddingPipeline:
         returns the event that marks ``out_host`` as complete (or call ``synchronize()``)."""
         if not (x_host.is_pinned() and out_host.is_pinned()):
             raise RuntimeError("EmbeddingPipeline.embed needs pinned host tensors (asynchronous copies)")
-        s = self._slot(x_host.shape, self._i % self.depth)
+        lane = self._i % len(self.lanes)
+        s = self._slot(x_host.shape, self._i % (self.depth * len(self.lanes)))
         self._i += 1
+        st = self.lanes[lane]
         with torch.cuda.stream(self.h2d):
             self.h2d.wait_event(s["free"])               # the previous forward that read this slot has finished
             s["x"].copy_(x_host, non_blocking=True)
             s["h2d_done"].record(self.h2d)
-        with torch.cuda.stream(self.compute):
-            self.compute.wait_event(s["h2d_done"])
-            emb = self.model(s["x"])
-            s["free"].record(self.compute)
-            s["emb_ready"].record(self.compute)
+        with torch.cuda.stream(st):
+            st.wait_event(s["h2d_done"])
+            emb = self.engines[lane].forward(s["x"], False)
+            s["free"].record(st)
+            s["emb_ready"].record(st)
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(s["emb_ready"])
             out_host.copy_(emb, non_blocking=True)
@@ -62,5 +86,6 @@ class EmbeddingPipeline:
 
     def synchronize(self):
         self.h2d.synchronize()
-        self.compute.synchronize()
+        for st in self.lanes:
+            st.synchronize()
         self.d2h.synchronize()
