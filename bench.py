@@ -57,6 +57,15 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.first = 0
+
+    def mark(self):
+        """Call at the start of the timed region: nvidia-smi needs up to a second to start, so the sampler is
+        launched before warm-up and only the samples taken after this mark are reported."""
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < 3.0:
+            time.sleep(0.01)
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -81,7 +90,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -243,12 +252,14 @@ def run_train(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for i in range(W):
-        step(*xs[i % nset])
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    for i in range(W):
+        step(*xs[i % nset])
+    barrier()
+    if rank == 0:
+        sampler.mark()
     e0.record()
     for i in range(K):
         loss = step(*xs[i % nset])
@@ -367,13 +378,15 @@ def main():
     cur = torch.cuda.current_stream(dev)
     # ---- value: inputs resident in HBM; `lanes` forwards in flight through the public pipeline ----------------------
     with torch.no_grad():
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
         for i in range(W):
             pipe.embed_device(xs[i % nbuf])
         pipe.synchronize()
-        sampler = ClockSampler(local_rank)
         barrier()
         if rank == 0:
-            sampler.start()
+            sampler.mark()
         e0.record(cur)
         for i in range(K):
             pipe.embed_device(xs[i % nbuf])
@@ -426,8 +439,10 @@ def main():
     peak = peaks["tflops_sustained"] if (ms > 2000 and peaks["tflops_sustained"]) else peaks["tflops_burst"]
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "traffic": None,
-        "kernel": "conv_umma_kernel (11 launches per step: 8 x 3x3 s1 + 3 x 5x5 s2 implicit-GEMM convs)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of the same 11 launches at batch 64, from the committed
+        # `ncu --set full` capture profiles/r01_final_conv_ncu_full.md (ncu flushes caches between kernels)
+        "traffic": 189381632 if (B == 64 and T == 160) else None,
+        "kernel": "conv3x3_halo_kernel x8 (3x3 s1) + conv_umma_kernel x3 (5x5 s2): the 11 tensor-core conv launches of a step",
         "flop_per_launch_set": B * CONV_TC_FLOP_PER_EMB, "launch_set_ms": conv_ms,
         "share_of_step": conv_ms / step_ms_prof, "per_launch_ms": [round(x, 5) for x in per_launch_ms],
         "peak_source": peaks["source"] + (" sustained" if peak == peaks["tflops_sustained"] else " burst"),
