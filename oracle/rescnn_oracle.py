@@ -220,3 +220,43 @@ def triplet_step_branch_a(sd, xa, xp, xn, margin: float, stats_out=None, storage
             if "running" in k:
                 stats_out[k] = cur[k]
     return loss.detach(), grads, outs[0].detach(), outs[1].detach(), outs[2].detach()
+
+
+def triplet_step_branch_b(sd, xa, xp, xn, label_p, label_n, margin: float, loss_ratio: float = 2.0, hard=None):
+    """Branch B of the training step (epoch <= min_softmax_epoch), train_triplet.py:215,251-291: three train-mode
+    forwards, margin mask -> hard indices, triplet loss on the DETACHED selected embeddings (constant w.r.t. the
+    parameters), second forward of the selected inputs through forward_classifier, cross-entropy over
+    cat[cls_a, cls_p, cls_n] against cat[label_p, label_p, label_n] (:283), loss = CE + loss_ratio * triplet (:287).
+    `hard` overrides the selection (used to compare implementations on identical indices).
+    Returns dict(hard, triplet, ce, loss, grads) or None when no triplet is selected (:263-264)."""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point
+              and "running" not in k}
+    cur = dict(sd)
+    cur.update(params)
+    outs = []
+    for x in (xa, xp, xn):                                                     # :215
+        st = {}
+        outs.append(forward(cur, x, True, st))
+        cur.update(st)
+    d_p = pairwise_distance(outs[0], outs[1])                                  # :251
+    d_n = pairwise_distance(outs[0], outs[2])                                  # :252
+    if hard is None:
+        hard = margin_select(d_p, d_n, margin)                                 # :253-262
+    if len(hard) == 0:
+        return None                                                            # :263-264
+    h = torch.from_numpy(np.asarray(hard))
+    sel = [o.detach()[h] for o in outs]                                        # :265-267 (numpy round trip detaches)
+    triplet = triplet_margin_loss(sel[0], sel[1], sel[2], margin)              # :275
+    logits = []
+    for x in (xa, xp, xn):                                                     # :277-279
+        st = {}
+        logits.append(forward_classifier(cur, x[h], True, st))
+        cur.update(st)
+    true = torch.cat([label_p[h], label_p[h], label_n[h]])                     # :283
+    ce = F.cross_entropy(torch.cat(logits), true)                              # :281-285
+    loss = ce + triplet * loss_ratio                                           # :287
+    loss.backward()                                                            # :290
+    grads = {k: v.grad for k, v in params.items()}
+    stats = {k: v for k, v in cur.items() if "running" in k}
+    return {"hard": np.asarray(hard), "triplet": triplet.detach(), "ce": ce.detach(), "loss": loss.detach(),
+            "grads": grads, "stats": stats}

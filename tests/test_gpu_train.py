@@ -136,3 +136,45 @@ def test_optimizer_step_is_picked_up(cuda_dev):
     l1, *_ = run_step(m, xa, xp, xn, margin=5.0)
     assert torch.isfinite(l0) and torch.isfinite(l1) and abs(l0.item() - l1.item()) > 0
     assert m.model.classifier.weight.grad is None
+
+
+def test_branch_b_step_matches_reference_golden(cuda_dev, golden_dir):
+    """train_triplet.py:215,251-291 with the drop-in classes: selection on the device, second forward through
+    forward_classifier, cross-entropy + 2 x (constant) triplet term, backward.  The reference's own selection
+    indices are used so that both sides differentiate the same samples."""
+    g = np.load(os.path.join(golden_dir, "branch_b_step.npz"))
+    B, T, s0, s1, s2, scale, lseed, margin = g["cfg"]
+    sd = O.make_state_dict(0, 16)
+    m = make_model(sd, "fp16", cuda_dev)
+    xa, xp, xn = (O.make_input(int(B), int(T), int(s), float(scale)).cuda() for s in (s0, s1, s2))
+    label_p, label_n = torch.from_numpy(g["label_p"]).cuda(), torch.from_numpy(g["label_n"]).cuda()
+    out_a, out_p, out_n = m(xa), m(xp), m(xn)                                            # :215
+    l2 = dsk.PairwiseDistance(2)
+    d_p, d_n = l2.forward(out_a, out_p), l2.forward(out_a, out_n)                        # :251-252
+    idx, cnt = dsk.select_hard_triplets(d_p, d_n, float(margin))                         # :253-262 on the device
+    k = int(cnt.item())
+    assert 0 < k <= int(B)
+    # the margin is the median of d_n - d_p, so the engine's fp16-level distance error may move a boundary sample
+    assert len(set(idx[:k].tolist()) ^ set(g["hard"].tolist())) <= 2
+    h = torch.from_numpy(g["hard"]).cuda()
+    sel = lambda t: t.detach()[h]                                                        # :265-274 (detached)
+    triplet = dsk.TripletMarginLoss(float(margin)).forward(sel(out_a), sel(out_p), sel(out_n))   # :275
+    cls = [m.forward_classifier(x[h].contiguous()) for x in (xa, xp, xn)]               # :277-279
+    true = torch.cat([label_p[h], label_p[h], label_n[h]])                               # :283
+    ce = torch.nn.CrossEntropyLoss()(torch.cat(cls), true)                               # :281-285
+    loss = ce + triplet * 2.0                                                            # :287
+    m.zero_grad()
+    loss.backward()                                                                      # :289-290
+    # batch of 2 selected utterances at T=32: BatchNorm statistics over 16 values per channel at stage 4 — the most
+    # ill-conditioned shape the path can see, hence the loose forward gates
+    assert abs(ce.item() - float(g["ce"])) <= 5e-2 * float(g["ce"])
+    assert abs(triplet.item() - float(g["triplet"])) <= 3e-2 * max(1.0, float(g["triplet"]))
+    checked = 0
+    for kname, p in m.named_parameters():
+        if "gnorm/" + kname not in g:
+            continue
+        assert p.grad is not None, kname
+        ref_norm = float(g["gnorm/" + kname])
+        assert abs(p.grad.double().norm().item() - ref_norm) <= 0.15 * ref_norm + 1e-9, (kname, p.grad.norm().item(), ref_norm)
+        checked += 1
+    assert checked == 40 and m.model.classifier.weight.grad is not None

@@ -120,3 +120,23 @@ def test_allpairs_matches_reference_distance(golden_dir):
     i2, v2 = O.allpairs_topk(E, labels, k)
     assert np.allclose(v2, val, rtol=1e-5)
     assert (i2 == idx).mean() > 0.98
+
+
+def test_branch_b_step_matches_reference(golden_dir):
+    """Selection -> forward_classifier -> cross-entropy step, train_triplet.py:251-291."""
+    g = np.load(os.path.join(golden_dir, "branch_b_step.npz"))
+    B, T, s0, s1, s2, scale, lseed, margin = g["cfg"]
+    sd = O.make_state_dict(0, 16)
+    xa, xp, xn = (O.make_input(int(B), int(T), int(s), float(scale)) for s in (s0, s1, s2))
+    r = O.triplet_step_branch_b(sd, xa, xp, xn, torch.from_numpy(g["label_p"]), torch.from_numpy(g["label_n"]), float(margin))
+    assert np.array_equal(r["hard"], g["hard"])
+    assert abs(r["ce"].item() - float(g["ce"])) < 1e-5 and abs(r["triplet"].item() - float(g["triplet"])) < 1e-5
+    assert abs(r["loss"].item() - float(g["loss"])) < 1e-5
+    n = 0
+    for k, gr in r["grads"].items():
+        if "gnorm/" + k not in g:
+            continue
+        ref_norm = float(g["gnorm/" + k])
+        assert abs(gr.double().norm().item() - ref_norm) <= 2e-3 * ref_norm + 1e-7, k
+        n += 1
+    assert n == 40        # the classifier now receives gradients too (SURVEY §0 fact 5)

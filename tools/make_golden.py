@@ -118,6 +118,47 @@ def golden_train():
     print("train_step.npz: loss", loss.item(), "params with grad", sum(1 for k in out if k.startswith("gnorm/")))
 
 
+def golden_branch_b():
+    """Branch-B step (train_triplet.py:215,251-291) with the reference model and its own forward_classifier."""
+    import torch.nn as nn
+    sd = O.make_state_dict(0, NUM_CLASSES)
+    m = ref_model(sd).train()
+    B, T = 6, 32
+    xa, xp, xn = (O.make_input(B, T, s, 3.0) for s in (30, 31, 32))
+    g = torch.Generator().manual_seed(33)
+    label_p = torch.randint(0, NUM_CLASSES, (B,), generator=g)
+    label_n = torch.randint(0, NUM_CLASSES, (B,), generator=g)
+    l2 = R.PairwiseDistance(2)
+    out_a, out_p, out_n = m(xa), m(xp), m(xn)                                   # :215
+    d_p = l2.forward(out_a, out_p)                                              # :251
+    d_n = l2.forward(out_a, out_n)                                              # :252
+    margin = float((d_n - d_p).median())                                        # a margin that selects about half
+    allm = (d_n - d_p < margin).cpu().data.numpy().flatten()                    # :253
+    hard = np.where(allm == 1)[0]                                               # :262
+    sel = lambda t: torch.from_numpy(t.cpu().data.numpy()[hard])                # :265-274
+    triplet = R.TripletMarginLoss(margin).forward(sel(out_a), sel(out_p), sel(out_n))   # :275
+    cls_a, cls_p, cls_n = (m.forward_classifier(sel(x)) for x in (xa, xp, xn))  # :277-279
+    true = torch.cat([label_p[hard], label_p[hard], label_n[hard]])             # :283
+    ce = nn.CrossEntropyLoss()(torch.cat([cls_a, cls_p, cls_n]), true)          # :281-285
+    loss = ce + triplet * 2.0                                                   # :287
+    m.zero_grad()
+    loss.backward()                                                             # :289-290
+    out = {"cfg": np.array([B, T, 30, 31, 32, 3.0, 33, margin]), "hard": hard.astype(np.int64),
+           "triplet": np.array(triplet.item(), np.float32), "ce": np.array(ce.item(), np.float32),
+           "loss": np.array(loss.item(), np.float32), "label_p": label_p.numpy(), "label_n": label_n.numpy()}
+    for k, v in m.named_parameters():
+        if v.grad is None:
+            continue
+        gflat = v.grad.flatten()
+        ix = sample_idx(gflat.numel(), 32)
+        out["gnorm/" + k] = np.array(gflat.double().norm().item())
+        out["gidx/" + k] = ix
+        out["gval/" + k] = gflat[ix].numpy()
+    np.savez(os.path.join(OUT, "branch_b_step.npz"), **out)
+    print("branch_b_step.npz: selected", len(hard), "of", B, "ce", ce.item(), "triplet", triplet.item(),
+          "params with grad", sum(1 for k in out if k.startswith("gnorm/")))
+
+
 def golden_allpairs():
     """Config 4 has no reference implementation: the fixture only pins the distance
     formula on pairs, computed with the reference's PairwiseDistance."""
@@ -130,6 +171,20 @@ def golden_allpairs():
     Dm = torch.stack([pd.forward(E[i:i + 1].expand(N, D), E) for i in range(N)])
     np.savez(os.path.join(OUT, "allpairs.npz"), seed=np.array([N, D, 3]), dist=Dm.numpy(), labels=labels.numpy())
     print("allpairs.npz", Dm.shape)
+
+
+def golden_verification():
+    """Best-threshold accuracy of the reference's own eval_metrics.evaluate on a fixed synthetic distance set."""
+    import eval_metrics as EM  # the reference's eval_metrics.py
+    g = np.random.RandomState(7)
+    labels = (np.arange(400) % 2 == 0)
+    distances = np.where(labels, g.normal(9.0, 2.0, 400), g.normal(13.0, 2.0, 400)).astype(np.float64)
+    # evaluate()'s VAL@FAR half (eval_metrics.py:10-12) raises under current scipy (interp1d on a FAR curve with
+    # duplicate x values); the accuracy half (:7-9 -> calculate_roc) is the part pinned here
+    tpr, fpr, acc = EM.calculate_roc(np.arange(0, 30, 0.01), distances, labels)
+    np.savez(os.path.join(OUT, "verification.npz"), distances=distances, labels=labels, ref_tpr=np.array(tpr),
+             ref_fpr=np.array(fpr), ref_accuracy=np.array(acc))
+    print("verification.npz: accuracy", acc, "tpr", tpr, "fpr", fpr)
 
 
 def golden_keys():
@@ -147,4 +202,6 @@ if __name__ == "__main__":
     golden_eval()
     golden_loss()
     golden_train()
+    golden_branch_b()
+    golden_verification()
     golden_allpairs()
