@@ -213,6 +213,45 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def run_allpairs(args, rank):
+    """BASELINE configs[3]: 1024-utterance all-pairs distance matrix + top-8 hard-negative select (single GPU,
+    launch-latency bound: reported in microseconds).  No reference implementation exists."""
+    if rank != 0:
+        return
+    import torch
+
+    from deepspeaker_pytorch_b200 import allpairs_topk
+
+    dev = torch.device("cuda", 0)
+    N, D, k = 1024, 512, 8
+    g = torch.Generator(device=dev).manual_seed(3)
+    sets = []
+    for _ in range(8):
+        E = torch.randn(N, D, device=dev, generator=g)
+        sets.append(10.0 * E / E.norm(dim=1, keepdim=True))
+    labels = (torch.arange(N, device=dev) // 16).long()
+    K, W = args.steps, args.warmup
+    for i in range(W):
+        allpairs_topk(sets[i % 8], labels, k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        idx, val = allpairs_topk(sets[i % 8], labels, k)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / K * 1e3
+    flop = 3.0 * N * N * D
+    line = {"metric": "microseconds per 1024-utterance all-pairs distance + top-8 select", "value": us, "unit": "us",
+            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": us / 1e3, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "1024 x 512 embeddings (norm 10), 64 speakers x 16, k=8, different-speaker candidates "
+                                   "(BASELINE configs[3])", "arithmetic": "fp32 direct differences (bit-exact indices vs the oracle)"},
+            "gflops": flop / (us * 1e-6) / 1e9,
+            "e2e": {"value": us, "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    emit(line)
+
+
 def run_train(args, rank, world, local_rank):
     """Triplet training step (restating train_triplet.py:215-224 with the drop-in classes): three train-mode
     forwards, TripletMarginLoss, backward, ONE gradient allreduce (N > 1), Adagrad step."""
@@ -320,7 +359,7 @@ def main():
     ap.add_argument("--frames", type=int, default=160)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=3, help="forwards in flight (compute streams) in the inference pipeline")
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "allpairs"],
                     help="infer: batch-64 embedding inference (BASELINE configs[1], the headline metric); "
                          "train: triplet training step, batch-128 triplets per GPU (configs[2]/[4])")
     args = ap.parse_args()
@@ -340,6 +379,9 @@ def main():
         return
     if args.workload == "train":
         run_train(args, rank, world, local_rank)
+        return
+    if args.workload == "allpairs":
+        run_allpairs(args, rank)
         return
 
     import torch

@@ -120,6 +120,7 @@ SIGNATURES = {
                                        c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dsk_margin_select": (c_int32, [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
     "dsk_gather_rows": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+    "dsk_allpairs_topk_tc": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dsk_allpairs_topk": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -181,6 +181,10 @@ struct dsk_handle_s {
   float* zeros = nullptr;  // [512] = 0
   float loss_scale = 0.f;  // 0 = automatic
   std::vector<dsk_train_ctx_s*> ctx_pool;
+  // cached all-pairs plan (buffers + Gram GEMM descriptors) for the last (N, D)
+  int ap_N = 0, ap_D = 0;
+  uint8_t* ap_buf = nullptr;
+  std::vector<ConvLaunch> ap_gemm;
   bool planar_s2 = false;      // eval forward: run the 5x5 s2 convs in the halo kernel's parity-planar form (DSK_PLANAR_S2=1)
   long long* trace = nullptr;  // debug: device buffer [3][512] for conv3x3_halo_kernel clock stamps
   // optional per-launch timing (dsk_set_profiling): events recorded around every kernel of a forward
@@ -858,6 +862,7 @@ int32_t dsk_destroy(dsk_handle h) {
   cudaFree(h->planar_perm);
   cudaFree(h->fc_wq);
   cudaFree(h->ws);
+  cudaFree(h->ap_buf);
   cudaFree(h->ones);
   cudaFree(h->zeros);
   for (dsk_train_ctx_s* c : h->ctx_pool) {
@@ -1543,6 +1548,8 @@ int32_t dsk_nhwc16_to_nchw_f32(dsk_handle h, const void* in, float* out, int32_t
 
 // ---- distances / loss / selection -----------------------------------------------------------------
 static inline float pd_eps(int D) { return static_cast<float>(1e-4 / static_cast<double>(D)); }
+int32_t dsk_allpairs_topk(const float* E, const int64_t* labels, int32_t N, int32_t D, int32_t k, int64_t* idx,
+                          float* val, void* stream);
 
 int32_t dsk_pairwise_distance(const float* x1, const float* x2, int32_t B, int32_t D, float* out, void* stream) {
   if (!x1 || !x2 || !out || B <= 0 || D <= 0) return fail(DSK_ERR_INVALID, "dsk_pairwise_distance: bad arguments");
@@ -1601,6 +1608,57 @@ int32_t dsk_gather_rows(const float* src, const int64_t* idx, const int32_t* cou
   dsk::gather_rows_kernel<<<max_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, idx, count, row_elems, out);
   KERNEL_CHECK();
   return DSK_OK;
+}
+
+int32_t dsk_allpairs_topk_tc(dsk_handle h, const float* E, const int64_t* labels, int32_t N, int32_t D, int32_t k,
+                             int64_t* idx, float* val, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!E || !labels || !idx || !val || N <= 0 || D <= 0 || k <= 0 || k > N)
+    return fail(DSK_ERR_INVALID, "dsk_allpairs_topk_tc: bad arguments");
+  if (D % 64 || k > 8) return dsk_allpairs_topk(E, labels, N, D, k, idx, val, stream);  // exact CUDA-core path
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Npad = (N + 127) / 128 * 128;
+  const size_t e16_bytes = static_cast<size_t>(Npad) * D * 2, g_bytes = static_cast<size_t>(Npad) * Npad * 4;
+  if (h->ap_N != N || h->ap_D != D) {
+    // (re)build the plan: buffers and the Gram GEMM descriptors.  Gram = E16 E16^T on the tensor cores: rows of E16
+    // are the "pixels" (W = 128, H = Npad/128) and also the "output channels" (<= 512 per launch); one tap, K = D
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (h->ap_buf) CUDA_TRY(cudaFree(h->ap_buf));
+    h->ap_buf = nullptr;
+    h->ap_N = h->ap_D = 0;
+    h->ap_gemm.clear();
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->ap_buf), e16_bytes + g_bytes + Npad * 4));
+    uint16_t* E16p = reinterpret_cast<uint16_t*>(h->ap_buf);
+    float* Gp = reinterpret_cast<float*>(h->ap_buf + e16_bytes);
+    TapTable tt;
+    tt.add(0, 0, 0, 0, 0);
+    for (int c0 = 0; c0 < Npad; c0 += 512) {
+      const int n_out = Npad - c0 < 512 ? Npad - c0 : 512;
+      ConvLaunch L;
+      rc = build_conv_core(h, &L, nhwc_view(E16p, 1, Npad / 128, 128, D), E16p + static_cast<size_t>(c0) * D, D, n_out, 1,
+                           nhwc_view(Gp, 1, Npad / 128, 128, Npad), nullptr, 1, Npad / 128, 128, tt, 0, 0.f, nullptr, nullptr,
+                           c0, 0, true);
+      if (rc) return rc;
+      h->ap_gemm.push_back(L);
+    }
+    h->ap_N = N;
+    h->ap_D = D;
+  }
+  uint16_t* E16 = reinterpret_cast<uint16_t*>(h->ap_buf);
+  float* G = reinterpret_cast<float*>(h->ap_buf + e16_bytes);
+  float* norms = reinterpret_cast<float*>(h->ap_buf + e16_bytes + g_bytes);
+  if (h->bf16) dsk::allpairs_prep_kernel<true><<<Npad, 128, 0, s>>>(E, N, D, E16, norms);
+  else dsk::allpairs_prep_kernel<false><<<Npad, 128, 0, s>>>(E, N, D, E16, norms);
+  KERNEL_CHECK();
+  for (size_t i = 0; i < h->ap_gemm.size() && !rc; ++i) rc = launch_conv(h, h->ap_gemm[i], s);
+  if (!rc) {
+    const float u = h->bf16 ? 1.0f / 256.0f : 1.0f / 2048.0f;  // unit roundoff of the 16-bit operand format
+    dsk::allpairs_select_refine_kernel<<<(N + 7) / 8, 256, 0, s>>>(E, G, norms, labels, N, Npad, D, pd_eps(D), k, u, idx, val);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(DSK_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  }
+  return rc;
 }
 
 int32_t dsk_allpairs_topk(const float* E, const int64_t* labels, int32_t N, int32_t D, int32_t k, int64_t* idx,

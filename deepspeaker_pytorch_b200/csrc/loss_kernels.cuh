@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dsk_ptx.cuh"
+
 namespace dsk {
 
 // Canonical row reduction used by every distance in this file:
@@ -217,6 +219,231 @@ __global__ void topk_rows_kernel(const float* __restrict__ S, const int64_t* __r
     }
     last_v = bv;
     last_j = bj;
+  }
+}
+
+}  // namespace dsk
+
+// =================================================================================================
+// Tensor-core all-pairs path: fp16 Gram on tcgen05 (conv_umma_kernel used as a plain GEMM, fp32 output), candidate
+// selection from the approximate distances, EXACT fp32 refinement of the candidates in the canonical order of
+// allpairs_sqdist_kernel (sequential-in-d fmaf), so the result is bit-identical to the exact path / the oracle.
+// =================================================================================================
+namespace dsk {
+
+// E fp32 [N][D] -> 16-bit [Npad][D] (rows >= N zero) + squared norms of the ROUNDED rows. One block per row.
+template <bool BF16>
+__global__ void allpairs_prep_kernel(const float* __restrict__ E, int N, int D, uint16_t* __restrict__ E16,
+                                     float* __restrict__ norms) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  float s = 0.f;
+  for (int t = threadIdx.x; t < D; t += blockDim.x) {
+    uint16_t h = 0;
+    if (row < N) {
+      h = to16<BF16>(E[static_cast<long>(row) * D + t]);
+      const float f = from16<BF16>(h);
+      s = fmaf(f, f, s);
+    }
+    E16[static_cast<long>(row) * D + t] = h;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    norms[row] = t;
+  }
+}
+
+constexpr int kApCand = 16;  // candidates refined exactly per row (must be >= k; host enforces k <= 8)
+
+__device__ __forceinline__ float exact_dist_seq(const float* __restrict__ a, const float* __restrict__ b, int D,
+                                                float eps) {
+  float acc = 0.f;
+  for (int t = 0; t < D; ++t) {
+    const float d = a[t] - b[t];
+    acc = fmaf(d, d, acc);
+  }
+  return sqrtf(acc + eps);
+}
+
+// One warp per row.  G: fp32 Gram of the rounded rows [Npad][Npad]; approximate squared distance
+// a_ij = n_i + n_j - 2 G_ij (exact squared distance of the ROUNDED rows up to fp32 accumulation).
+// Exactness argument: rounding row e to 16 bit moves it by at most u*||e|| (u = unit roundoff), so for every pair
+//   | a_ij - ||e_i - e_j||^2 | <= 2 d r + r^2 + slack,   r = u (||e_i|| + max_j ||e_j||),  d = ||e_i - e_j||.
+// If the worst kept candidate's a exceeds (k-th exact distance)^2 by more than that bound, no discarded column can
+// beat the k-th result and the refined top-k is the exact answer; otherwise the warp scans the whole row exactly.
+__global__ void __launch_bounds__(256)
+allpairs_select_refine_kernel(const float* __restrict__ E, const float* __restrict__ G, const float* __restrict__ norms,
+                              const int64_t* __restrict__ labels, int N, int Npad, int D, float eps, int k, float u,
+                              int64_t* __restrict__ idx, float* __restrict__ val) {
+  __shared__ int cand_j[8][kApCand];
+  __shared__ float cand_a[8][kApCand];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + w;
+  if (row >= N) return;
+  const float* g = G + static_cast<long>(row) * Npad;
+  const float ni = norms[row];
+  const int64_t my_label = labels[row];
+  const float INF = __int_as_float(0x7f800000);
+  // ---- candidates: the kApCand smallest approximate distances, extracted in lexicographic (a, j) order.
+  // Rows of up to 1024 columns keep their 32 values per lane in registers; longer rows re-read G (L1/L2 hits).
+  constexpr int kRegCols = 32;
+  const bool in_regs = N <= 32 * kRegCols;
+  float areg[kRegCols];
+  if (in_regs) {
+#pragma unroll
+    for (int q = 0; q < kRegCols; ++q) {
+      const int j = lane + 32 * q;
+      areg[q] = (j < N && labels[j] != my_label) ? (ni + norms[j]) - 2.0f * g[j] : INF;
+    }
+  }
+  float last_a = -INF;
+  int last_j = -1;
+  for (int t = 0; t < kApCand; ++t) {
+    float ba = INF;
+    int bj = 0x7fffffff;
+    if (in_regs) {
+#pragma unroll
+      for (int q = 0; q < kRegCols; ++q) {
+        const int j = lane + 32 * q;
+        const float a = areg[q];
+        const bool after = (a > last_a) || (a == last_a && j > last_j);
+        if (a < INF && after && (a < ba || (a == ba && j < bj))) {
+          ba = a;
+          bj = j;
+        }
+      }
+    } else {
+      for (int j = lane; j < N; j += 32) {
+        if (labels[j] == my_label) continue;
+        const float a = (ni + norms[j]) - 2.0f * g[j];
+        const bool after = (a > last_a) || (a == last_a && j > last_j);
+        if (after && (a < ba || (a == ba && j < bj))) {
+          ba = a;
+          bj = j;
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float oa = __shfl_xor_sync(0xffffffffu, ba, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (oa < ba || (oa == ba && oj < bj)) {
+        ba = oa;
+        bj = oj;
+      }
+    }
+    if (lane == 0) {
+      cand_j[w][t] = bj;
+      cand_a[w][t] = ba;
+    }
+    last_a = ba;
+    last_j = bj;
+  }
+  __syncwarp();
+  // ---- exact refinement of the candidates (lane t < kApCand owns candidate t)
+  float v = INF;
+  int j = 0x7fffffff;
+  if (lane < kApCand && cand_j[w][lane] != 0x7fffffff) {
+    j = cand_j[w][lane];
+    v = exact_dist_seq(E + static_cast<long>(row) * D, E + static_cast<long>(j) * D, D, eps);
+  }
+  // k-th smallest exact value among the candidates
+  float kth = INF;
+  {
+    float lv = -1.f;
+    int lj = -1;
+    for (int t = 0; t < k; ++t) {
+      float bv = INF;
+      int bj = 0x7fffffff;
+      const bool after = (v > lv) || (v == lv && j > lj);
+      if (after) {
+        bv = v;
+        bj = j;
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ov < bv || (ov == bv && oj < bj)) {
+          bv = ov;
+          bj = oj;
+        }
+      }
+      lv = bv;
+      lj = bj;
+      kth = bv;
+    }
+  }
+  // safe iff every column NOT among the candidates has approximate squared distance >= kth^2 + bound
+  const float worst_a = cand_a[w][kApCand - 1];
+  float nmax = 0.f;
+  for (int jj = lane; jj < N; jj += 32) nmax = fmaxf(nmax, norms[jj]);
+  for (int o = 16; o > 0; o >>= 1) nmax = fmaxf(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+  const float r = u * (sqrtf(ni) + sqrtf(nmax)) * 1.01f;
+  const float dmax = sqrtf(fmaxf(worst_a, 0.f)) + r + 1e-3f;
+  const float tol = 2.f * dmax * r + r * r + 1e-5f * (ni + nmax) + 1e-4f;
+  const bool all_candidates = cand_j[w][kApCand - 1] == 0x7fffffff;  // fewer valid columns than candidates
+  const bool safe = all_candidates || (worst_a >= (kth * kth - eps) + tol);
+  if (!safe) {
+    // ---- exact fallback: scan the whole row (rare); same arithmetic as the exact path
+    float lv = -1.f;
+    int lj = -1;
+    for (int t = 0; t < k; ++t) {
+      float bv = INF;
+      int bj = 0x7fffffff;
+      for (int jj = lane; jj < N; jj += 32) {
+        if (labels[jj] == my_label) continue;
+        const float vv = exact_dist_seq(E + static_cast<long>(row) * D, E + static_cast<long>(jj) * D, D, eps);
+        const bool after = (vv > lv) || (vv == lv && jj > lj);
+        if (after && (vv < bv || (vv == bv && jj < bj))) {
+          bv = vv;
+          bj = jj;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ov < bv || (ov == bv && oj < bj)) {
+          bv = ov;
+          bj = oj;
+        }
+      }
+      if (lane == 0) {
+        idx[static_cast<long>(row) * k + t] = (bj == 0x7fffffff) ? -1 : bj;
+        val[static_cast<long>(row) * k + t] = bv;
+      }
+      lv = bv;
+      lj = bj;
+    }
+    return;
+  }
+  // ---- final top-k among the exactly refined candidates, (value, index) lexicographic
+  float lv = -1.f;
+  int lj = -1;
+  for (int t = 0; t < k; ++t) {
+    float bv = INF;
+    int bj = 0x7fffffff;
+    const bool after = (v > lv) || (v == lv && j > lj);
+    if (after) {
+      bv = v;
+      bj = j;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (ov < bv || (ov == bv && oj < bj)) {
+        bv = ov;
+        bj = oj;
+      }
+    }
+    if (lane == 0) {
+      idx[static_cast<long>(row) * k + t] = (bj == 0x7fffffff) ? -1 : bj;
+      val[static_cast<long>(row) * k + t] = bv;
+    }
+    lv = bv;
+    lj = bj;
   }
 }
 

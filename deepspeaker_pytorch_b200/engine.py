@@ -205,7 +205,21 @@ def gather_rows(src, idx, count):
     return out
 
 
-def allpairs_topk(E, labels, k):
+_AP_HANDLES = {}
+
+
+def _allpairs_handle(device):
+    """Module-level fp16 engine handle for the tensor-core all-pairs path (one per device)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _AP_HANDLES:
+        h = ctypes.c_void_p()
+        L.check(L.load().dsk_create(ctypes.byref(h), key, L.DSK_F16), "dsk_create")
+        _AP_HANDLES[key] = h
+    return _AP_HANDLES[key]
+
+
+def allpairs_topk(E, labels, k, exact_cuda_cores: bool = False):
+    """exact_cuda_cores=True forces the all-fp32 CUDA-core path; the default tensor-core path returns the same bits."""
     if not E.is_cuda:
         raise RuntimeError("CUDA tensors required")
     E = E.detach().float().contiguous()
@@ -214,6 +228,10 @@ def allpairs_topk(E, labels, k):
     idx = torch.empty(N, k, device=E.device, dtype=torch.int64)
     val = torch.empty(N, k, device=E.device, dtype=torch.float32)
     with torch.cuda.device(E.device):
-        L.check(L.load().dsk_allpairs_topk(E.data_ptr(), labels.data_ptr(), N, D, k, idx.data_ptr(), val.data_ptr(),
-                                           L.cur_stream()), "dsk_allpairs_topk")
+        if exact_cuda_cores:
+            L.check(L.load().dsk_allpairs_topk(E.data_ptr(), labels.data_ptr(), N, D, k, idx.data_ptr(), val.data_ptr(),
+                                               L.cur_stream()), "dsk_allpairs_topk")
+        else:
+            L.check(L.load().dsk_allpairs_topk_tc(_allpairs_handle(E.device), E.data_ptr(), labels.data_ptr(), N, D, k,
+                                                  idx.data_ptr(), val.data_ptr(), L.cur_stream()), "dsk_allpairs_topk_tc")
     return idx, val

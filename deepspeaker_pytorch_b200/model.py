@@ -164,6 +164,7 @@ def select_hard_triplets(d_p, d_n, margin):
     return _engine.margin_select(d_p, d_n, margin)
 
 
-def allpairs_topk(E, labels, k):
-    """BASELINE config 4: per-row k nearest different-label embeddings (idx int64 (N,k), dist fp32 (N,k))."""
-    return _engine.allpairs_topk(E, labels, k)
+def allpairs_topk(E, labels, k, exact_cuda_cores=False):
+    """BASELINE config 4: per-row k nearest different-label embeddings (idx int64 (N,k), dist fp32 (N,k)).
+    Default: tcgen05 Gram GEMM + exact fp32 refinement (bit-identical to the all-fp32 path, `exact_cuda_cores=True`)."""
+    return _engine.allpairs_topk(E, labels, k, exact_cuda_cores)

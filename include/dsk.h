@@ -189,6 +189,11 @@ int32_t dsk_gather_rows(const float* src, const int64_t* idx, const int32_t* cou
  * implementation exists — defined from PairwiseDistance, model.py:13-18):
  * D[i][j] = sqrt(sum_d (E[i]-E[j])^2 + 1e-4/Dim), candidates j with labels[j] != labels[i];
  * ties broken by lower j. Writes idx (N,k) int64 and val (N,k) fp32, ascending distance. */
+/* Same result (bit-identical indices and values), computed with a tcgen05 fp16 Gram GEMM + candidate selection + exact
+ * fp32 refinement of the k+8 best candidates per row (exact row scan on the device when the safety margin is not met).
+ * Falls back to dsk_allpairs_topk when D % 64 != 0 or k > 8. */
+int32_t dsk_allpairs_topk_tc(dsk_handle h, const float* E, const int64_t* labels, int32_t N, int32_t D, int32_t k,
+                             int64_t* idx, float* val, void* stream);
 int32_t dsk_allpairs_topk(const float* E, const int64_t* labels, int32_t N, int32_t D, int32_t k, int64_t* idx,
                           float* val, void* stream);
 

@@ -85,10 +85,12 @@ def test_allpairs_topk_bit_exact_vs_oracle(cuda_dev, N, k, groups):
     E_ = torch.randn(N, 512, generator=g)
     E_ = 10.0 * E_ / E_.norm(dim=1, keepdim=True)
     labels = (torch.arange(N) % groups).long()
-    idx, val = dsk.allpairs_topk(E_.cuda(), labels.cuda(), k)
+    idx, val = dsk.allpairs_topk(E_.cuda(), labels.cuda(), k)                             # tcgen05 Gram + exact refinement
     oidx, oval = C.allpairs_topk(E_.numpy(), labels.numpy(), k)
     assert np.array_equal(idx.cpu().numpy(), oidx)
     assert np.array_equal(val.cpu().numpy(), oval)
+    idx2, val2 = dsk.allpairs_topk(E_.cuda(), labels.cuda(), k, exact_cuda_cores=True)    # all-fp32 CUDA-core path
+    assert torch.equal(idx2, idx) and torch.equal(val2, val)
     # properties: never the same speaker, ascending, symmetric distances
     assert bool((labels[idx.cpu()] != labels.view(-1, 1)).all())
     assert bool((val[:, 1:] >= val[:, :-1]).all())
@@ -96,3 +98,22 @@ def test_allpairs_topk_bit_exact_vs_oracle(cuda_dev, N, k, groups):
     cos = (E_ @ E_.t()) / 100.0
     d_cos = torch.sqrt(torch.clamp(200.0 * (1 - cos), min=0) + 1e-4 / 512)
     assert torch.allclose(torch.gather(d_cos, 1, idx.cpu()), val.cpu(), atol=2e-3)
+
+
+def test_allpairs_tc_path_near_duplicates_and_small_groups(cuda_dev):
+    """Adversarial inputs for the candidate/refine scheme: near-duplicate rows (distance gaps below the fp16 Gram
+    error -> the exact fallback must kick in), fewer valid columns than candidates, N not a multiple of 128."""
+    g = torch.Generator().manual_seed(9)
+    base = torch.randn(40, 512, generator=g)
+    E_ = base.repeat_interleave(5, dim=0) + 1e-4 * torch.randn(200, 512, generator=g)     # clusters of near-duplicates
+    E_ = 10.0 * E_ / E_.norm(dim=1, keepdim=True)
+    labels = (torch.arange(200) % 3).long()
+    for k in (1, 4, 8):
+        idx, val = dsk.allpairs_topk(E_.cuda(), labels.cuda(), k)
+        oidx, oval = C.allpairs_topk(E_.numpy(), labels.numpy(), k)
+        assert np.array_equal(idx.cpu().numpy(), oidx) and np.array_equal(val.cpu().numpy(), oval)
+    E2 = 10.0 * torch.nn.functional.normalize(torch.randn(20, 512, generator=g), dim=1)
+    lab2 = torch.tensor([0] * 14 + [1] * 6)
+    idx, val = dsk.allpairs_topk(E2.cuda(), lab2.cuda(), 5)                               # 6 valid columns for label 0
+    oidx, oval = C.allpairs_topk(E2.numpy(), lab2.numpy(), 5)
+    assert np.array_equal(idx.cpu().numpy(), oidx) and np.array_equal(val.cpu().numpy(), oval)
