@@ -53,6 +53,8 @@ struct HaloParams {
   float clip_hi;
   const float* scale;
   const float* bias;
+  int plain3x3;           // MMA issuer plan: 1 = 3x3 (HaloPlan<1>), 2 = planar 5x5 s2 (HaloPlan<2>), 0 = walk the tables
+  int late_trigger;       // release the dependent kernel when this CTA starts its last tile instead of at entry
   int b_resident;         // all weight boxes of a CTA's channel tile fit the B ring: load once
   unsigned pitch_magic, img_magic;  // floor(2^32/d)+1 for d = W+1 and H+1: q/d == __umulhi(q, magic) for q < 2^32/d
   long long* trace;       // debug: per-role clock64 stamps of CTA 0 (nullptr = off); [role 0..2][512]
@@ -64,12 +66,33 @@ struct HaloParams {
     if (p.trace && blockIdx.x == 0 && (idx) < 512) p.trace[(role) * 512 + (idx)] = clock64(); \
   } while (0)
 
+// Compile-time K-loop plans for the MMA issuer (the producer still walks the runtime tables, which say the same).
+// KIND 1: 3x3, one plane, boxes = filter rows.  KIND 2: planar 5x5 s2, packed tap n = 3*box + t, planes start at
+// packed taps 0 / 9 / 15 / 21 and have 3x3, 3x2, 2x3, 2x2 taps; tap (i, j) of a plane reads halo row i*(W+1) + j.
+template <int KIND>
+struct HaloPlan {
+  static constexpr int kBoxes = KIND == 1 ? 3 : 9;
+  __host__ __device__ static constexpr int plane_of(int n) { return KIND == 1 ? 0 : (n < 9 ? 0 : n < 15 ? 1 : n < 21 ? 2 : 3); }
+  __host__ __device__ static constexpr int plane_start(int pl) { return pl == 0 ? 0 : pl == 1 ? 9 : pl == 2 ? 15 : 21; }
+  __host__ __device__ static constexpr int cols(int pl) { return (KIND == 2 && (pl & 1)) ? 2 : 3; }
+  __host__ __device__ static constexpr int ntaps(int b) { return (KIND == 2 && b == 8) ? 1 : 3; }
+  __host__ __device__ static constexpr bool first(int b) { return KIND == 1 ? b == 0 : (b == 0 || b == 3 || b == 5 || b == 7); }
+  __host__ __device__ static constexpr bool last(int b) { return KIND == 1 ? b == 2 : (b == 2 || b == 4 || b == 6 || b == 8); }
+  __host__ __device__ static constexpr int row_i(int b, int t) {
+    return (3 * b + t - plane_start(plane_of(3 * b + t))) / cols(plane_of(3 * b + t));
+  }
+  __host__ __device__ static constexpr int col_j(int b, int t) {
+    return (3 * b + t - plane_start(plane_of(3 * b + t))) % cols(plane_of(3 * b + t));
+  }
+};
+
 template <int N_TILE>
 struct HaloSmem {
   static constexpr int kBStageBytes = 3 * N_TILE * 128;      // one weight box: 3 taps
   static constexpr int kScaleBiasBytes = 2 * 512 * 4;
   static constexpr int kAccStages = 4;                       // TMEM accumulators: 4 x N_TILE <= 512 columns
-  static constexpr int kFixedBytes = kScaleBiasBytes + 512 + 1024;  // scale/bias + barriers + alignment slack
+  static constexpr int kRowDstBytes = 2 * 128 * 8;                  // planar output: per-row destination, two tiles
+  static constexpr int kFixedBytes = kScaleBiasBytes + kRowDstBytes + 512 + 1024;  // + barriers + alignment slack
   static int total(int a_stage_bytes, int a_stages, int b_stages, int stg_bufs, int res_bufs) {
     return a_stages * a_stage_bytes + b_stages * kBStageBytes + (stg_bufs + res_bufs) * kATileBytes + kFixedBytes;
   }
@@ -113,7 +136,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   uint8_t* smem_res = smem_stg + p.stg_bufs * kATileBytes;
   float* smem_scale = reinterpret_cast<float*>(smem_res + p.res_bufs * kATileBytes);
   float* smem_bias = smem_scale + 512;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_scale) + S::kScaleBiasBytes);
+  uint16_t** row_dst = reinterpret_cast<uint16_t**>(reinterpret_cast<uint8_t*>(smem_scale) + S::kScaleBiasBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(row_dst) + S::kRowDstBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kHaloMaxStages;
   uint64_t* b_full = a_empty + kHaloMaxStages;
@@ -126,26 +150,64 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  pdl_launch_dependents();
+  if (threadIdx.x == 0) DSK_TRACE(0, 480);
+  if (!p.late_trigger) pdl_launch_dependents();
   const int pitch = p.W + 1;
   const int halo_rows = kTileM + 2 * p.W + 4;
   const int num_tiles = p.tiles_m * p.tiles_c;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmIn);
-    tma_prefetch_desc(&tmW);
-    tma_prefetch_desc(&tmOut);
-    if (p.flags & CONV_RESIDUAL) tma_prefetch_desc(&tmRes);
+  // channel tile slowest: a CTA's consecutive tiles (stride gridDim.x) mostly share the weight tile
+  auto decode = [&](int tile, int& c0, int& q0) {
+    const int ct = tile / p.tiles_m;
+    const int mt = tile - ct * p.tiles_m;
+    c0 = ct * N_TILE;
+    q0 = p.q_begin + mt * kTileM;
+  };
+
+  // The producer warp owns the operand barriers and starts the first loads before the CTA-wide setup barrier: weight
+  // boxes at once (parameters), the first halo tile right after the dependency wait.  The TMEM allocation and the
+  // scale/bias fetch (a global-memory round trip) then overlap the first operand fetch instead of preceding it.
+  int pre_b = 0;  // weight boxes of the first tile already issued (producer warp only)
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmIn);
+      tma_prefetch_desc(&tmW);
+      for (int i = 0; i < kAStages; ++i) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&a_empty[i], 1);
+      }
+      for (int i = 0; i < kBStages; ++i) {
+        mbar_init(&b_full[i], 1);
+        mbar_init(&b_empty[i], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    if (static_cast<int>(blockIdx.x) < num_tiles) {
+      int c0, q0;
+      decode(blockIdx.x, c0, q0);
+      const int total_b = p.nboxes * p.chunks;
+      pre_b = total_b < kBStages ? total_b : kBStages;
+      if (elect_one_sync()) {
+        for (int i = 0; i < pre_b; ++i) {
+          const int ch = i / p.nboxes, b = i - ch * p.nboxes;
+          mbar_arrive_expect_tx(&b_full[i], S::kBStageBytes);
+          tma_load_3d(smem_b + i * S::kBStageBytes, &tmW, &b_full[i], ch * 64, c0, p.box_wtap[b]);
+        }
+      }
+      __syncwarp();
+      pdl_wait();  // activations of the previous kernel are read below
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&a_full[0], halo_rows * 128);
+        tma_load_2d(smem_a, &tmIn, &a_full[0], 0, p.box_plane[0] * p.plane_positions + q0 - (p.W + 2));
+        DSK_TRACE(0, 0);
+      }
+      __syncwarp();
+    }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kAStages; ++i) {
-      mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
-    }
-    for (int i = 0; i < kBStages; ++i) {
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
-    }
+    tma_prefetch_desc(&tmOut);
+    if (p.flags & CONV_RESIDUAL) tma_prefetch_desc(&tmRes);
     for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
@@ -168,49 +230,52 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_wait();  // everything above touched only parameters; activations of the previous kernel are read/written below
-
-  // channel tile slowest: a CTA's consecutive tiles (stride gridDim.x) mostly share the weight tile
-  auto decode = [&](int tile, int& c0, int& q0) {
-    const int ct = tile / p.tiles_m;
-    const int mt = tile - ct * p.tiles_m;
-    c0 = ct * N_TILE;
-    q0 = p.q_begin + mt * kTileM;
-  };
+  if (threadIdx.x == 0) DSK_TRACE(0, 481);
+  pdl_wait();  // everything above (but the producer's first halo tile) touched only parameters
+  if (threadIdx.x == 0) DSK_TRACE(0, 482);
 
   if (warp == 0) {
     // ===================== TMA producer (warp-converged loop, one elected lane issues) =====================
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     bool first = true;
-    int tcount = 0;
+    int tcount = 1;
+    bool a_pre = true;  // the first halo tile was issued in the prologue
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int c0, q0;
       decode(tile, c0, q0);
       for (int ch = 0; ch < p.chunks; ++ch) {
         for (int b = 0; b < p.nboxes; ++b) {
           if (p.box_first[b]) {
-            mbar_wait(&a_empty[as], aph ^ 1);
-            if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&a_full[as], halo_rows * 128);
-              tma_load_2d(smem_a + as * p.a_stage_bytes, &tmIn, &a_full[as], ch * 64,
-                          p.box_plane[b] * p.plane_positions + q0 - (p.W + 2));
-              DSK_TRACE(0, tcount);
-              ++tcount;
+            if (a_pre) {
+              a_pre = false;
+            } else {
+              mbar_wait(&a_empty[as], aph ^ 1);
+              if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&a_full[as], halo_rows * 128);
+                tma_load_2d(smem_a + as * p.a_stage_bytes, &tmIn, &a_full[as], ch * 64,
+                            p.box_plane[b] * p.plane_positions + q0 - (p.W + 2));
+                DSK_TRACE(0, tcount);
+                ++tcount;
+              }
+              __syncwarp();
             }
-            __syncwarp();
             if (++as == kAStages) {
               as = 0;
               aph ^= 1;
             }
           }
           if (!p.b_resident || first) {
-            mbar_wait(&b_empty[bs], bph ^ 1);
-            if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&b_full[bs], S::kBStageBytes);
-              tma_load_3d(smem_b + bs * S::kBStageBytes, &tmW, &b_full[bs], ch * 64, c0, p.box_wtap[b]);
+            if (pre_b > 0) {
+              --pre_b;
+            } else {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&b_full[bs], S::kBStageBytes);
+                tma_load_3d(smem_b + bs * S::kBStageBytes, &tmW, &b_full[bs], ch * 64, c0, p.box_wtap[b]);
+              }
+              __syncwarp();
             }
-            __syncwarp();
             if (++bs == kBStages) {
               bs = 0;
               bph ^= 1;
@@ -234,6 +299,84 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       tc_fence_after();
       if (lane == 0) DSK_TRACE(1, tcount * 4 + 0);
       const uint32_t d_tmem = tmem_base + acc * N_TILE;
+      if (p.plain3x3 == 1 && p.b_resident) {
+        // 64-channel 3x3: all nine weight taps stay resident; one straight-line burst of 36 MMAs per tile.
+        // Straight-line issue matters: descriptors are base + compile-time offsets + i*pitch, nothing is read from the
+        // tables between MMAs (the tensor pipe's queue drains while a table-driven issuer computes its next operands).
+        mbar_wait(&a_full[as], aph);
+        tc_fence_after();
+        if (lane == 0) DSK_TRACE(1, tcount * 4 + 1);
+        if (first) {
+          for (int b = 0; b < 3; ++b) mbar_wait(&b_full[b], 0);
+          tc_fence_after();
+        }
+        if (elect_one_sync()) {
+          const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a + as * p.a_stage_bytes));
+          const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b));
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            const uint64_t dab = da0 + static_cast<uint64_t>(b * pitch) * 8;
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(d_tmem, dab + (t * 8 + 2 * k), db0 + ((b * 3 + t) * (N_TILE * 8) + 2 * k), idesc,
+                         (b > 0 || t > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&a_empty[as]);
+          umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++as == kAStages) {
+          as = 0;
+          aph ^= 1;
+        }
+      } else if (p.plain3x3) {
+        auto issue_chunks = [&](auto plan_tag) {
+          using Plan = decltype(plan_tag);
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            uint64_t da0 = 0;
+#pragma unroll
+            for (int b = 0; b < Plan::kBoxes; ++b) {
+              if (Plan::first(b)) {
+                mbar_wait(&a_full[as], aph);
+                tc_fence_after();
+                if (lane == 0 && ch == 0 && b == 0) DSK_TRACE(1, tcount * 4 + 1);
+                da0 = umma_desc_sw128(smem_u32(smem_a + as * p.a_stage_bytes));
+              }
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              if (elect_one_sync()) {
+                const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b + bs * S::kBStageBytes));
+#pragma unroll
+                for (int t = 0; t < Plan::ntaps(b); ++t) {
+                  const uint64_t da = da0 + static_cast<uint64_t>(Plan::row_i(b, t) * pitch + Plan::col_j(b, t)) * 8;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16(d_tmem, da + 2 * k, db0 + (t * (N_TILE * 8) + 2 * k), idesc,
+                             (b > 0 || t > 0 || k > 0) ? 1u : (ch > 0 ? 1u : 0u));
+                }
+                umma_commit(&b_empty[bs]);
+                if (Plan::last(b)) umma_commit(&a_empty[as]);
+                if (b == Plan::kBoxes - 1 && ch == p.chunks - 1) umma_commit(&tmem_full[acc]);
+              }
+              __syncwarp();
+              if (++bs == kBStages) {
+                bs = 0;
+                bph ^= 1;
+              }
+              if (Plan::last(b)) {
+                if (++as == kAStages) {
+                  as = 0;
+                  aph ^= 1;
+                }
+              }
+            }
+          }
+        };
+        if (p.plain3x3 == 1) issue_chunks(HaloPlan<1>{});
+        else issue_chunks(HaloPlan<2>{});
+      } else
       for (int ch = 0; ch < p.chunks; ++ch) {
         uint64_t da0 = 0;
         for (int b = 0; b < p.nboxes; ++b) {
@@ -344,7 +487,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         const long plane = (hh & 1) * 2 + (ww & 1);
         planar_row = p.out_ptr + (plane * p.out_plane_positions + q2) * p.out_C + c0;
       }
+      // published before the first chunk barrier of this tile; two tables because a fast thread may enter the next
+      // tile while others still copy this one out
+      if (p.out_planar && half == 0) row_dst[(ecount & 1) * 128 + row] = planar_row;
       if (etid == 0) DSK_TRACE(2, ecount * 8 + 0);
+      if (p.late_trigger && tile + static_cast<int>(gridDim.x) >= num_tiles) pdl_launch_dependents();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (etid == 0) DSK_TRACE(2, ecount * 8 + 1);
@@ -398,12 +545,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           o.y = pack2<BF16>(f[2], f[3]);
           o.z = pack2<BF16>(f[4], f[5]);
           o.w = pack2<BF16>(f[6], f[7]);
-          if (p.out_planar) {
-            if (!junk) *reinterpret_cast<uint4*>(planar_row + (j * 64 + half * 32 + qq * 8)) = o;
-          } else {
-            if (junk) o = make_uint4(0u, 0u, 0u, 0u);  // pad positions stay zero
-            *slot = o;
-          }
+          if (junk) o = make_uint4(0u, 0u, 0u, 0u);  // pad positions stay zero
+          *slot = o;
         }
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 5);
         fence_proxy_async_smem();
@@ -416,9 +559,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           }
         }
         named_bar_sync(1, 256);
-        if (etid == 0 && !p.out_planar) {
-          tma_store_2d(&tmOut, stg, c0 + j * 64, q0);
-          tma_store_commit();
+        if (!p.out_planar) {
+          if (etid == 0) {
+            tma_store_2d(&tmOut, stg, c0 + j * 64, q0);
+            tma_store_commit();
+          }
+        } else {
+          // parity-planar destination: rows scatter over four planes, so no TMA box; 8 lanes copy one 128-byte row
+          // (full lines per warp store), 4 rows per thread
+          const int chunk = etid & 7;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 32 + (etid >> 3);
+            uint16_t* d = row_dst[(ecount & 1) * 128 + rr];
+            if (d != nullptr)
+              *reinterpret_cast<uint4*>(d + j * 64 + chunk * 8) =
+                  *reinterpret_cast<const uint4*>(stg + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+          }
         }
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 6);
         if (++buf == p.stg_bufs) buf = 0;
@@ -438,6 +595,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DSK_TRACE(0, 483);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

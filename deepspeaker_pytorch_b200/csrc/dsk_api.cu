@@ -15,6 +15,7 @@
 #include "../../include/dsk.h"
 #include "conv_umma.cuh"
 #include "conv3x3_halo.cuh"
+#include "conv1_umma.cuh"
 #include "loss_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "train_kernels.cuh"
@@ -50,7 +51,15 @@ int fail(int code, const char* fmt, ...) {
 
 // Launch with the programmatic-stream-serialization attribute (PDL). Only for kernels that call pdl_wait().
 template <typename... KArgs, typename... Args>
+cudaError_t launch_opt(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args);
+
+template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  return launch_opt(true, kern, grid, block, smem, s, static_cast<Args&&>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_opt(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -60,7 +69,7 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
@@ -158,6 +167,7 @@ struct dsk_handle_s {
   void* wpk_planar[DSK_NUM_CONV] = {}; // 16-bit [plane-major tap][cout][cin] for the halo form of the 5x5 s2 convs
   int* planar_perm = nullptr;         // device copy of the plane-major tap order
   float* conv1_w = nullptr;           // fp32 [64][25]
+  uint16_t* conv1_img = nullptr;      // pre-swizzled hi/lo split operand image of conv1_umma_kernel (16 KB)
   float* scale[DSK_NUM_CONV] = {};    // folded eval BN
   float* bias[DSK_NUM_CONV] = {};
   float* fc_wq = nullptr;             // fp32 [E][w*512+c]
@@ -172,8 +182,37 @@ struct dsk_handle_s {
     std::vector<void*> act;  // 12 activation buffers (16-bit NHWC), index = conv index
     float* pooled = nullptr;
     float* fc_out = nullptr;
+    float* fc_part = nullptr;  // [kFcSplit][B][E] K-slice partial sums of the fc layer
     std::vector<ConvLaunch> conv;  // index = conv index (0 unused): the 5x5 s2 stage-entry convs
     std::vector<HaloLaunch> halo;  // index = conv index: the 3x3 s1 block convs (padded layout)
+    // The 15 launches of a forward as one CUDA graph (captured from the second call of a shape on; programmatic
+    // dependent-launch edges included): one cudaGraphLaunch per forward instead of 15 kernel launches.  Only the input
+    // and output pointers differ between calls: they are patched into the first / last kernel node.
+    bool warm = false, graph_failed = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    cudaGraphNode_t node_first = nullptr, node_last = nullptr;
+    const float* g_x = nullptr;
+    float* g_emb = nullptr;
+    Plan() = default;
+    Plan(const Plan&) = delete;
+    Plan& operator=(const Plan&) = delete;
+    Plan(Plan&& o) noexcept { *this = std::move(o); }
+    Plan& operator=(Plan&& o) noexcept {
+      B = o.B; T = o.T; act = std::move(o.act); pooled = o.pooled; fc_out = o.fc_out; fc_part = o.fc_part;
+      conv = std::move(o.conv); halo = std::move(o.halo); warm = o.warm; graph_failed = o.graph_failed;
+      graph = o.graph; gexec = o.gexec; node_first = o.node_first; node_last = o.node_last; g_x = o.g_x; g_emb = o.g_emb;
+      o.graph = nullptr; o.gexec = nullptr;
+      return *this;
+    }
+    void reset_graph() {
+      if (gexec) cudaGraphExecDestroy(gexec);
+      if (graph) cudaGraphDestroy(graph);
+      gexec = nullptr;
+      graph = nullptr;
+      graph_failed = false;
+    }
+    ~Plan() { reset_graph(); }
   };
   std::map<std::pair<int, int>, Plan> plans;
   // training
@@ -185,7 +224,10 @@ struct dsk_handle_s {
   int ap_N = 0, ap_D = 0;
   uint8_t* ap_buf = nullptr;
   std::vector<ConvLaunch> ap_gemm;
-  bool planar_s2 = false;      // eval forward: run the 5x5 s2 convs in the halo kernel's parity-planar form (DSK_PLANAR_S2=1)
+  bool use_graph = true;       // DSK_GRAPH=0: always launch the forward kernel by kernel
+  bool conv1_pdl = true;       // debug knob DSK_CONV1_PDL=0: launch conv1 with plain stream serialisation
+  bool late_trigger = false;   // debug knob DSK_LATE_TRIGGER=1: halo kernels release their dependents at the last tile
+  bool planar_s2 = true;       // eval forward: run the 5x5 s2 convs in the halo kernel's parity-planar form (DSK_PLANAR_S2=0: generic kernel)
   long long* trace = nullptr;  // debug: device buffer [3][512] for conv3x3_halo_kernel clock stamps
   // optional per-launch timing (dsk_set_profiling): events recorded around every kernel of a forward
   bool profiling = false;
@@ -204,7 +246,7 @@ struct dsk_train_ctx_s {
   void* y[DSK_NUM_CONV] = {};          // after BN (+res) + clip (16-bit NHWC)
   float* mean[DSK_NUM_CONV] = {};
   float* rstd[DSK_NUM_CONV] = {};
-  float *pooled = nullptr, *fc_out = nullptr, *inv_norm = nullptr;
+  float *pooled = nullptr, *fc_out = nullptr, *fc_part = nullptr, *inv_norm = nullptr;
   float *scale_t = nullptr, *shift_t = nullptr, *partial = nullptr, *coef = nullptr;
   float *g_fc = nullptr, *dP = nullptr, *dwacc = nullptr, *c1part = nullptr;
   void *gA = nullptr, *gB = nullptr, *G = nullptr, *gres = nullptr;
@@ -592,6 +634,7 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   p.scale = scale;
   p.bias = bias;
   p.trace = h->trace;
+  p.late_trigger = h->late_trigger ? 1 : 0;
   p.pitch_magic = static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(W + 1)) + 1u;
   p.img_magic = static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(H + 1)) + 1u;
   const long npos = padded_positions(N, H, W);
@@ -634,6 +677,8 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
     p.nboxes = nb;  // 3 + 2 + 2 + 2 = 9
   }
   // all weight boxes of a CTA fit the B ring and every tile of the CTA uses the same ones: load them once
+  p.plain3x3 = ksize == 3 ? 1 : 2;
+  if (getenv("DSK_HALO_TABLE_ISSUE")) p.plain3x3 = 0;  // debug: table-driven MMA issue
   p.b_resident = (p.chunks == 1 && p.tiles_c == 1 && p.nboxes <= 3 && n_tile == 64) ? 1 : 0;
   p.out_planar = out_planar;
   if (out_planar) {
@@ -753,6 +798,8 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
   bytes += static_cast<size_t>(B) * 2048 * 4;
   const size_t off_fc = bytes;
   bytes += static_cast<size_t>(B) * h->emb * 4;
+  const size_t off_fc_part = bytes;
+  bytes += static_cast<size_t>(dsk::kFcSplit) * B * h->emb * 4;
   if (bytes > h->ws_bytes) {
     // drop cached plans: their descriptors point into the old workspace
     h->plans.clear();
@@ -775,6 +822,7 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
   for (int i = 0; i < DSK_NUM_CONV; ++i) pl.act[i] = base + off[i];
   pl.pooled = reinterpret_cast<float*>(base + off_pooled);
   pl.fc_out = reinterpret_cast<float*>(base + off_fc);
+  pl.fc_part = reinterpret_cast<float*>(base + off_fc_part);
   pl.conv.resize(DSK_NUM_CONV);
   pl.halo.resize(DSK_NUM_CONV);
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
@@ -831,8 +879,14 @@ int32_t dsk_create(dsk_handle* out, int32_t device, int32_t operand) {
   h->bf16 = operand == DSK_BF16;
   h->num_sms = prop.multiProcessorCount;
   {
-    const char* e = getenv("DSK_PLANAR_S2");
-    h->planar_s2 = e && e[0] == '1';
+    const char* e = getenv("DSK_PLANAR_S2");  // default on; DSK_PLANAR_S2=0 runs the 5x5 s2 convs in the generic tap kernel
+    h->planar_s2 = !(e && e[0] == '0');
+    e = getenv("DSK_GRAPH");
+    h->use_graph = !(e && e[0] == '0');
+    e = getenv("DSK_CONV1_PDL");
+    h->conv1_pdl = !(e && e[0] == '0');
+    e = getenv("DSK_LATE_TRIGGER");
+    h->late_trigger = e && e[0] == '1';
   }
   {
     std::vector<float> one(512, 1.0f);
@@ -859,6 +913,7 @@ int32_t dsk_destroy(dsk_handle h) {
     cudaFree(h->bias[i]);
   }
   cudaFree(h->conv1_w);
+  cudaFree(h->conv1_img);
   cudaFree(h->planar_perm);
   cudaFree(h->fc_wq);
   cudaFree(h->ws);
@@ -882,6 +937,7 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
     return fail(DSK_ERR_INVALID, "dsk_load_weights: embedding_size must be a positive multiple of 64");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (h->weights_loaded && h->emb != w->embedding_size) return fail(DSK_ERR_INVALID, "embedding_size changed");
+  for (auto& kv : h->plans) kv.second.reset_graph();  // captured graphs hold borrowed parameter pointers (fc bias)
   h->emb = w->embedding_size;
   for (int i = 0; i < DSK_NUM_CONV; ++i) {
     const LayerCfg c = layer_cfg(i);
@@ -905,6 +961,10 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
         if (rc) return rc;
       }
       CUDA_TRY(cudaMemcpyAsync(h->conv1_w, w->conv_w[0], 64 * 25 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      if (!h->conv1_img) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->conv1_img), dsk::kConv1ImgHalfs * 2));
+      if (h->bf16) dsk::pack_conv1_umma_kernel<true><<<32, 256, 0, s>>>(h->conv1_w, h->conv1_img);
+      else dsk::pack_conv1_umma_kernel<false><<<32, 256, 0, s>>>(h->conv1_w, h->conv1_img);
+      KERNEL_CHECK();
       continue;
     }
     if (!h->wpk[i]) {
@@ -949,18 +1009,11 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
   return DSK_OK;
 }
 
-int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, int32_t mode,
-                           void* stream) {
-  int rc = check_handle(h);
-  if (rc) return rc;
-  if (!h->weights_loaded) return fail(DSK_ERR_STATE, "dsk_rescnn_forward: call dsk_load_weights first");
-  if (!x || !emb || B <= 0) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: bad arguments");
-  if (T < 16 || T % 16) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: T must be a positive multiple of 16 (got %d)", T);
-  if (mode != DSK_EVAL) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: use dsk_rescnn_forward_train for batch-statistics BN");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  dsk_handle_s::Plan* pl;
-  rc = get_plan(h, B, T, &pl);
-  if (rc) return rc;
+namespace {
+
+// the 15 launches of one eval forward on stream s
+int enqueue_forward(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B, int T, float* emb, cudaStream_t s) {
+  int rc = 0;
   h->n_marks = 0;
   auto mark = [&]() {
     if (!h->profiling) return;
@@ -974,14 +1027,13 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
   mark();
   // conv1 (+bn1 +clip)
   {
-    const int hout = T / 2;
-    const int blocks = B * ((hout + 7) / 8);
+    const int blocks = B * (T / 2 / 4);  // 4 output rows x 32 pixels per CTA
     if (h->bf16)
-      CUDA_TRY(launch_pdl(dsk::conv1_kernel<true, false>, dim3(blocks), dim3(256), 0, s, x, (const float*)h->conv1_w,
-                          (const float*)h->scale[0], (const float*)h->bias[0], pl->act[0], T, 1, 20.0f, 1));
+      CUDA_TRY(launch_opt(h->conv1_pdl, dsk::conv1_umma_kernel<true>, dim3(blocks), dim3(128), 0, s, x, (const uint4*)h->conv1_img,
+                          (const float*)h->scale[0], (const float*)h->bias[0], (uint16_t*)pl->act[0], T, 20.0f));
     else
-      CUDA_TRY(launch_pdl(dsk::conv1_kernel<false, false>, dim3(blocks), dim3(256), 0, s, x, (const float*)h->conv1_w,
-                          (const float*)h->scale[0], (const float*)h->bias[0], pl->act[0], T, 1, 20.0f, 1));
+      CUDA_TRY(launch_opt(h->conv1_pdl, dsk::conv1_umma_kernel<false>, dim3(blocks), dim3(128), 0, s, x, (const uint4*)h->conv1_img,
+                          (const float*)h->scale[0], (const float*)h->bias[0], (uint16_t*)pl->act[0], T, 20.0f));
     mark();
   }
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
@@ -999,21 +1051,145 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
       CUDA_TRY(launch_pdl(dsk::pool_time_kernel<false>, dim3(B, WC / 512), dim3(256), 0, s, (const uint16_t*)pl->act[11],
                           pl->pooled, H4, WC, 512, 1));
     mark();
+    const int fc_smem = (dsk::kFcUtt + dsk::kFcFeat) * dsk::kFcPitch * 4;
     static bool fc_attr = false;
-    const int fc_smem = dsk::kFcUtt * 2048 * 4;
     if (!fc_attr) {
       CUDA_TRY(cudaFuncSetAttribute(dsk::fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem));
       fc_attr = true;
     }
-    dim3 g((B + dsk::kFcUtt - 1) / dsk::kFcUtt, h->emb / 16);
-    CUDA_TRY(launch_pdl(dsk::fc_kernel, g, dim3(256), fc_smem, s, (const float*)pl->pooled, (const float*)h->fc_wq, h->fc_b,
-                        pl->fc_out, B, 2048, h->emb));
+    dim3 g((B + dsk::kFcUtt - 1) / dsk::kFcUtt, h->emb / dsk::kFcFeat, dsk::kFcSplit);
+    CUDA_TRY(launch_pdl(dsk::fc_kernel, g, dim3(256), fc_smem, s, (const float*)pl->pooled, (const float*)h->fc_wq,
+                        pl->fc_part, B, 2048, h->emb));
     mark();
-    CUDA_TRY(launch_pdl(dsk::l2norm_kernel, dim3(B), dim3(128), 0, s, (const float*)pl->fc_out, emb, (float*)nullptr, h->emb,
-                        10.0f));
+    CUDA_TRY(launch_pdl(dsk::l2norm_kernel, dim3(B), dim3(512), 0, s, (const float*)pl->fc_part, (int)dsk::kFcSplit,
+                        (const float*)h->fc_b, pl->fc_out, emb, (float*)nullptr, B, h->emb, 10.0f));
     mark();
   }
   return DSK_OK;
+}
+
+void conv1_node_params(dsk_handle h, dsk_handle_s::Plan* pl, int B, int T, cudaKernelNodeParams* kp) {
+  memset(kp, 0, sizeof(*kp));
+  kp->func = h->bf16 ? reinterpret_cast<void*>(dsk::conv1_umma_kernel<true>) : reinterpret_cast<void*>(dsk::conv1_umma_kernel<false>);
+  kp->gridDim = dim3(B * (T / 2 / 4));
+  kp->blockDim = dim3(128);
+}
+
+// Capture the forward into a graph (stream capture keeps the programmatic-launch edges).  Any failure just leaves the
+// plan on the kernel-by-kernel path.
+void build_forward_graph(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B, int T, float* emb, cudaStream_t s) {
+  pl->graph_failed = true;  // until proven otherwise
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  const int rc = enqueue_forward(h, pl, x, B, T, emb, s);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(s, &g);
+  if (rc || e != cudaSuccess || !g) {
+    cudaGetLastError();
+    if (g) cudaGraphDestroy(g);
+    return;
+  }
+  size_t n = 0;
+  if (cudaGraphGetNodes(g, nullptr, &n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    cudaGraphDestroy(g);
+    return;
+  }
+  std::vector<cudaGraphNode_t> nodes(n);
+  cudaGraphGetNodes(g, nodes.data(), &n);
+  cudaKernelNodeParams c1;
+  conv1_node_params(h, pl, B, T, &c1);
+  cudaGraphNode_t first = nullptr, last = nullptr;
+  for (size_t i = 0; i < n; ++i) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
+    cudaKernelNodeParams kp;
+    if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+    if (kp.func == c1.func) first = nodes[i];
+    if (kp.func == reinterpret_cast<void*>(dsk::l2norm_kernel)) last = nodes[i];
+  }
+  cudaGraphExec_t ex = nullptr;
+  if (!first || !last || cudaGraphInstantiate(&ex, g, 0) != cudaSuccess) {
+    cudaGetLastError();
+    cudaGraphDestroy(g);
+    return;
+  }
+  pl->graph = g;
+  pl->gexec = ex;
+  pl->node_first = first;
+  pl->node_last = last;
+  pl->g_x = x;
+  pl->g_emb = emb;
+  pl->graph_failed = false;
+}
+
+// patch the input / output pointers of the instantiated graph
+int retarget_forward_graph(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B, int T, float* emb) {
+  if (x != pl->g_x) {
+    cudaKernelNodeParams kp;
+    conv1_node_params(h, pl, B, T, &kp);
+    const uint4* wimg = reinterpret_cast<const uint4*>(h->conv1_img);
+    const float *sc = h->scale[0], *bi = h->bias[0];
+    uint16_t* out = static_cast<uint16_t*>(pl->act[0]);
+    int Tv = T;
+    float clip = 20.0f;
+    void* args[7] = {&x, &wimg, &sc, &bi, &out, &Tv, &clip};
+    kp.kernelParams = args;
+    CUDA_TRY(cudaGraphExecKernelNodeSetParams(pl->gexec, pl->node_first, &kp));
+    pl->g_x = x;
+  }
+  if (emb != pl->g_emb) {
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = reinterpret_cast<void*>(dsk::l2norm_kernel);
+    kp.gridDim = dim3(B);
+    kp.blockDim = dim3(512);
+    const float* part = pl->fc_part;
+    int nsplit = dsk::kFcSplit;
+    const float* fb = h->fc_b;
+    float* y = pl->fc_out;
+    float* inv = nullptr;
+    int Bv = B, E = h->emb;
+    float alpha = 10.0f;
+    void* args[9] = {&part, &nsplit, &fb, &y, &emb, &inv, &Bv, &E, &alpha};
+    kp.kernelParams = args;
+    CUDA_TRY(cudaGraphExecKernelNodeSetParams(pl->gexec, pl->node_last, &kp));
+    pl->g_emb = emb;
+  }
+  return DSK_OK;
+}
+
+}  // namespace
+
+int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, int32_t mode,
+                           void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!h->weights_loaded) return fail(DSK_ERR_STATE, "dsk_rescnn_forward: call dsk_load_weights first");
+  if (!x || !emb || B <= 0) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: bad arguments");
+  if (T < 16 || T % 16) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: T must be a positive multiple of 16 (got %d)", T);
+  if (mode != DSK_EVAL) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: use dsk_rescnn_forward_train for batch-statistics BN");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dsk_handle_s::Plan* pl;
+  rc = get_plan(h, B, T, &pl);
+  if (rc) return rc;
+  if (h->use_graph && !h->profiling && !h->trace && pl->warm) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) cudaGetLastError();
+    if (cs == cudaStreamCaptureStatusNone) {  // inside a caller's capture the plain launches are what gets recorded
+      if (!pl->gexec && !pl->graph_failed) build_forward_graph(h, pl, x, B, T, emb, s);
+      if (pl->gexec) {
+        rc = retarget_forward_graph(h, pl, x, B, T, emb);
+        if (rc) return rc;
+        CUDA_TRY(cudaGraphLaunch(pl->gexec, s));
+        return DSK_OK;
+      }
+    }
+  }
+  pl->warm = true;  // the first call of a shape also sets the one-time function attributes, outside any capture
+  return enqueue_forward(h, pl, x, B, T, emb, s);
 }
 
 int32_t dsk_set_profiling(dsk_handle h, int32_t enable) {
@@ -1067,6 +1243,7 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
     o_rstd[i] = take(C * 4);
   }
   const size_t o_pooled = take(static_cast<size_t>(B) * 2048 * 4), o_fc = take(static_cast<size_t>(B) * h->emb * 4);
+  const size_t o_fc_part = take(static_cast<size_t>(dsk::kFcSplit) * B * h->emb * 4);
   const size_t o_inv = take(B * 4), o_sc = take(512 * 4), o_sh = take(512 * 4);
   const size_t o_part = take(static_cast<size_t>(kStatBlocksMax) * 2 * 512 * 4), o_coef = take(3 * 512 * 4);
   const size_t o_gfc = take(static_cast<size_t>(B) * h->emb * 4), o_dP = take(static_cast<size_t>(B) * 2048 * 4);
@@ -1083,6 +1260,7 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
   }
   c->pooled = reinterpret_cast<float*>(b + o_pooled);
   c->fc_out = reinterpret_cast<float*>(b + o_fc);
+  c->fc_part = reinterpret_cast<float*>(b + o_fc_part);
   c->inv_norm = reinterpret_cast<float*>(b + o_inv);
   c->scale_t = reinterpret_cast<float*>(b + o_sc);
   c->shift_t = reinterpret_cast<float*>(b + o_sh);
@@ -1200,12 +1378,12 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
     if (bf) dsk::pool_time_kernel<true><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC, 512, 0);
     else dsk::pool_time_kernel<false><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC, 512, 0);
     KERNEL_CHECK();
-    const int fc_smem = dsk::kFcUtt * 2048 * 4;
+    const int fc_smem = (dsk::kFcUtt + dsk::kFcFeat) * dsk::kFcPitch * 4;
     CUDA_TRY(cudaFuncSetAttribute(dsk::fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem));
-    dim3 g((B + dsk::kFcUtt - 1) / dsk::kFcUtt, h->emb / 16);
-    dsk::fc_kernel<<<g, 256, fc_smem, s>>>(c->pooled, h->fc_wq, h->fc_b, c->fc_out, B, 2048, h->emb);
+    dim3 g((B + dsk::kFcUtt - 1) / dsk::kFcUtt, h->emb / dsk::kFcFeat, dsk::kFcSplit);
+    dsk::fc_kernel<<<g, 256, fc_smem, s>>>(c->pooled, h->fc_wq, c->fc_part, B, 2048, h->emb);
     KERNEL_CHECK();
-    dsk::l2norm_kernel<<<B, 128, 0, s>>>(c->fc_out, emb, c->inv_norm, h->emb, 10.0f);
+    dsk::l2norm_kernel<<<B, 512, 0, s>>>(c->fc_part, dsk::kFcSplit, h->fc_b, c->fc_out, emb, c->inv_norm, B, h->emb, 10.0f);
     KERNEL_CHECK();
   }
   c->forward_done = true;

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]*/, const float* __restrict__ scale,
              const float* __restrict__ bias, void* __restrict__ out, int T, int do_clip, float clip_hi, int padded) {
   constexpr int WIN = 64, WOUT = 32, ROWS = 8, PATCH_ROWS = 2 * ROWS + 3, PATCH_W = WIN + 4;
-  __shared__ float patch[PATCH_ROWS][PATCH_W];
+  __shared__ __align__(16) float patch[PATCH_ROWS][PATCH_W];  // PATCH_W * 4 B is a multiple of 16
   __shared__ float wsm[64 * 25];
   pdl_launch_dependents();
   pdl_wait();  // the output buffer may still be read by the previous forward's kernels
@@ -127,28 +127,40 @@ conv1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][25]
   // padded NHWC layout (conv3x3_halo.cuh): row n*(H+1)+h+1, W+1 pixels per row, column 0 is the zero pad
   const long pix0 = padded ? (static_cast<long>(n) * (hout + 1) + oh + 1) * (WOUT + 1) + 1
                            : (static_cast<long>(n) * hout + oh) * WOUT;
-#pragma unroll 2
-  for (int ow = 0; ow < WOUT; ++ow) {
-    float a0 = 0.f, a1 = 0.f;
+  // four output pixels per iteration: their 5x11 input window is 3 aligned float4 broadcast loads per filter row
+  // (15 shared loads feed 200 FMAs; one load per tap would make the loop load-issue bound)
+#pragma unroll 1
+  for (int ow = 0; ow < WOUT; ow += 4) {
+    float a[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q][0] = a[q][1] = 0.f;
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
+      const float4* prow = reinterpret_cast<const float4*>(&patch[2 * warp + r][2 * ow]);
+      const float4 v0 = prow[0], v1 = prow[1], v2 = prow[2];
+      const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
 #pragma unroll
       for (int s = 0; s < 5; ++s) {
-        const float v = patch[2 * warp + r][2 * ow + s];
-        a0 = fmaf(v, w0[r * 5 + s], a0);
-        a1 = fmaf(v, w1[r * 5 + s], a1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a[q][0] = fmaf(v[2 * q + s], w0[r * 5 + s], a[q][0]);
+          a[q][1] = fmaf(v[2 * q + s], w1[r * 5 + s], a[q][1]);
+        }
       }
     }
-    a0 = fmaf(a0, s0, b0);
-    a1 = fmaf(a1, s1, b1);
-    if (do_clip) {
-      a0 = fminf(fmaxf(a0, 0.f), clip_hi);
-      a1 = fminf(fmaxf(a1, 0.f), clip_hi);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float a0 = fmaf(a[q][0], s0, b0);
+      float a1 = fmaf(a[q][1], s1, b1);
+      if (do_clip) {
+        a0 = fminf(fmaxf(a0, 0.f), clip_hi);
+        a1 = fminf(fmaxf(a1, 0.f), clip_hi);
+      }
+      if constexpr (OUT_F32)
+        reinterpret_cast<float2*>(out)[(pix0 + ow + q) * 32 + lane] = make_float2(a0, a1);
+      else
+        o32[(pix0 + ow + q) * 32 + lane] = pack2<BF16>(a0, a1);
     }
-    if constexpr (OUT_F32)
-      reinterpret_cast<float2*>(out)[(pix0 + ow) * 32 + lane] = make_float2(a0, a1);
-    else
-      o32[(pix0 + ow) * 32 + lane] = pack2<BF16>(a0, a1);
   }
 }
 
@@ -207,91 +219,104 @@ __global__ void pack_fc_weight_kernel(const float* __restrict__ w /*[E][C*4+w]*/
   }
 }
 
-// y[b][e] = sum_k pooled[b][k] * wq[e][k] + bias[e].  grid (ceil(B/16), E/16), block 256 = 8 warps.
-// Block = 16 utterances x 16 output features: the 16 pooled vectors (128 KB fp32) sit in shared memory, every warp
-// owns two features whose 8 KB weight rows are streamed once, coalesced, two loads deep; lane l covers the float4
-// columns l, l+32, ... .  Traffic: weights read B/16 times, pooled vectors E/16 times (4x less than an 8x8 split).
-constexpr int kFcUtt = 16;
+// part[z][b][e] = sum_{k in slice z} pooled[b][k] * wq[e][k].  grid (ceil(B/64), E/32, kFcSplit), block 256.
+// Block = 64 utterances x 32 output features x one K slice of 128: both operand slices sit in shared memory (rows
+// padded by 4 floats so that the float4 reads of 8 consecutive rows hit 8 different bank groups); thread = 4 utterances
+// x 2 features (f and f+16), six float4 shared loads per 32 FMAs.  Operand traffic from L2 is (64+32)*128*4 B per
+// block, 12 MB per forward at B=64 (a 16x16 tile moves 32 MB and was bandwidth-bound at 15 us).  The K split gives the
+// tail 256 blocks; the slices are summed in fixed order (plus the bias) by l2norm_kernel, so the result does not
+// depend on scheduling.
+constexpr int kFcUtt = 64, kFcFeat = 32, kFcSlice = 128, kFcSplit = 2048 / kFcSlice, kFcPitch = kFcSlice + 4;
 __global__ void __launch_bounds__(256)
-fc_kernel(const float* __restrict__ pooled, const float* __restrict__ wq, const float* __restrict__ bias,
-          float* __restrict__ y, int B, int K, int E) {
-  extern __shared__ float sp[];  // [kFcUtt][K]
-  const int b0 = blockIdx.x * kFcUtt;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int e0 = blockIdx.y * 16 + warp * 2;
-  const float4* w0 = reinterpret_cast<const float4*>(wq + static_cast<long>(e0) * K);
-  const float4* w1 = reinterpret_cast<const float4*>(wq + static_cast<long>(e0 + 1) * K);
-  const int n4 = K / 4;
+fc_kernel(const float* __restrict__ pooled, const float* __restrict__ wq, float* __restrict__ part, int B, int K, int E) {
+  extern __shared__ __align__(16) float fc_smem[];
+  float* sp = fc_smem;                      // [kFcUtt][kFcPitch]
+  float* sw = fc_smem + kFcUtt * kFcPitch;  // [kFcFeat][kFcPitch]
+  const int b0 = blockIdx.x * kFcUtt, e0 = blockIdx.y * kFcFeat, k0 = blockIdx.z * kFcSlice;
+  const int tid = threadIdx.x;
   pdl_launch_dependents();
-  float4 a0 = w0[lane], a1 = w1[lane];  // parameters: safe before the dependency wait
-  pdl_wait();
-  // shared-memory fill: warp w copies utterances w and w+8, eight independent 16-byte loads in flight per lane
-  for (int u = warp; u < kFcUtt; u += 8) {
-    const bool ok = b0 + u < B;
-    const float4* src = reinterpret_cast<const float4*>(pooled + static_cast<long>(ok ? b0 + u : 0) * K);
-    float4* dst = reinterpret_cast<float4*>(sp) + u * n4;
-    for (int i0 = lane; i0 < n4; i0 += 256) {
-      float4 t[8];
+  // fill: (64 + 32) rows x 32 float4; thread = float4 column (tid & 31) of rows (tid >> 5) + 8 i; all loads in flight
+  {
+    const int c4 = tid & 31, r0 = tid >> 5;
+    float4 tw[kFcFeat / 8], tp[kFcUtt / 8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) t[j] = (ok && i0 + 32 * j < n4) ? src[i0 + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < kFcFeat / 8; ++i)  // parameters: safe before the dependency wait
+      tw[i] = reinterpret_cast<const float4*>(wq + static_cast<long>(e0 + r0 + 8 * i) * K + k0)[c4];
+    pdl_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (i0 + 32 * j < n4) dst[i0 + 32 * j] = t[j];
+    for (int i = 0; i < kFcUtt / 8; ++i) {
+      const int u = b0 + r0 + 8 * i;
+      tp[i] = u < B ? reinterpret_cast<const float4*>(pooled + static_cast<long>(u) * K + k0)[c4]
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int i = 0; i < kFcFeat / 8; ++i) reinterpret_cast<float4*>(sw + (r0 + 8 * i) * kFcPitch)[c4] = tw[i];
+#pragma unroll
+    for (int i = 0; i < kFcUtt / 8; ++i) reinterpret_cast<float4*>(sp + (r0 + 8 * i) * kFcPitch)[c4] = tp[i];
   }
   __syncthreads();
-  float acc0[kFcUtt], acc1[kFcUtt];
+  const int tf = tid & 15, tu = tid >> 4;  // features tf, tf+16; utterances 4*tu .. 4*tu+3
+  float acc[4][2];
 #pragma unroll
-  for (int u = 0; u < kFcUtt; ++u) acc0[u] = acc1[u] = 0.f;
-  for (int i = lane; i < n4; i += 32) {
-    float4 n0 = a0, n1 = a1;
-    if (i + 32 < n4) {
-      n0 = w0[i + 32];
-      n1 = w1[i + 32];
-    }
+  for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.f;
+  const float4* w0 = reinterpret_cast<const float4*>(sw + tf * kFcPitch);
+  const float4* w1 = reinterpret_cast<const float4*>(sw + (tf + 16) * kFcPitch);
+  const float4* p0 = reinterpret_cast<const float4*>(sp + (4 * tu) * kFcPitch);
+#pragma unroll 4
+  for (int k4 = 0; k4 < kFcSlice / 4; ++k4) {
+    const float4 a = w0[k4], b = w1[k4];
 #pragma unroll
-    for (int u = 0; u < kFcUtt; ++u) {
-      const float4 pv = reinterpret_cast<const float4*>(sp + u * K)[i];
-      acc0[u] = fmaf(a0.x, pv.x, acc0[u]);
-      acc0[u] = fmaf(a0.y, pv.y, acc0[u]);
-      acc0[u] = fmaf(a0.z, pv.z, acc0[u]);
-      acc0[u] = fmaf(a0.w, pv.w, acc0[u]);
-      acc1[u] = fmaf(a1.x, pv.x, acc1[u]);
-      acc1[u] = fmaf(a1.y, pv.y, acc1[u]);
-      acc1[u] = fmaf(a1.z, pv.z, acc1[u]);
-      acc1[u] = fmaf(a1.w, pv.w, acc1[u]);
+    for (int u = 0; u < 4; ++u) {
+      const float4 pv = p0[u * (kFcPitch / 4) + k4];
+      acc[u][0] = fmaf(a.x, pv.x, acc[u][0]);
+      acc[u][0] = fmaf(a.y, pv.y, acc[u][0]);
+      acc[u][0] = fmaf(a.z, pv.z, acc[u][0]);
+      acc[u][0] = fmaf(a.w, pv.w, acc[u][0]);
+      acc[u][1] = fmaf(b.x, pv.x, acc[u][1]);
+      acc[u][1] = fmaf(b.y, pv.y, acc[u][1]);
+      acc[u][1] = fmaf(b.z, pv.z, acc[u][1]);
+      acc[u][1] = fmaf(b.w, pv.w, acc[u][1]);
     }
-    a0 = n0;
-    a1 = n1;
   }
+  float* pz = part + static_cast<long>(blockIdx.z) * B * E;
 #pragma unroll
-  for (int u = 0; u < kFcUtt; ++u)
-    for (int o = 16; o > 0; o >>= 1) {
-      acc0[u] += __shfl_xor_sync(0xffffffffu, acc0[u], o);
-      acc1[u] += __shfl_xor_sync(0xffffffffu, acc1[u], o);
+  for (int u = 0; u < 4; ++u) {
+    const int ub = b0 + 4 * tu + u;
+    if (ub < B) {
+      pz[static_cast<long>(ub) * E + e0 + tf] = acc[u][0];
+      pz[static_cast<long>(ub) * E + e0 + tf + 16] = acc[u][1];
     }
-  if (lane == 0) {
-    const float bb0 = bias[e0], bb1 = bias[e0 + 1];
-#pragma unroll
-    for (int u = 0; u < kFcUtt; ++u)
-      if (b0 + u < B) {
-        y[static_cast<long>(b0 + u) * E + e0] = acc0[u] + bb0;
-        y[static_cast<long>(b0 + u) * E + e0 + 1] = acc1[u] + bb1;
-      }
   }
 }
 
+// y[b][:] = bias + sum_z part[z][b][:] (fixed order; written out for the backward pass), then
 // out[b][:] = alpha * y[b][:] / sqrt(sum(y^2) + 1e-10)   (/root/reference/model.py:172-183,210-213)
 // also writes inv_norm[b] = 1/sqrt(sum+1e-10) when inv_norm != nullptr (saved for backward).
-__global__ void l2norm_kernel(const float* __restrict__ y, float* __restrict__ out, float* __restrict__ inv_norm,
-                              int E, float alpha) {
+__global__ void l2norm_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ bias,
+                              float* __restrict__ y, float* __restrict__ out, float* __restrict__ inv_norm, int B, int E,
+                              float alpha) {
   __shared__ float red[32];
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
-  const float* yr = y + static_cast<long>(b) * E;
+  float* yr = y + static_cast<long>(b) * E;
   float s = 0.f;
-  for (int i = threadIdx.x; i < E; i += blockDim.x) s = fmaf(yr[i], yr[i], s);
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    float v = bias[i];
+    const float* pp = part + static_cast<long>(b) * E + i;
+    const long zs = static_cast<long>(B) * E;
+    int z = 0;
+    for (; z + 8 <= nsplit; z += 8) {  // eight independent loads, added in slice order
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = pp[(z + j) * zs];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v += t[j];
+    }
+    for (; z < nsplit; ++z) v += pp[z * zs];
+    yr[i] = v;  // re-read below by the same thread
+    s = fmaf(v, v, s);
+  }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
