@@ -1247,7 +1247,7 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
   const size_t o_inv = take(B * 4), o_sc = take(512 * 4), o_sh = take(512 * 4);
   const size_t o_part = take(static_cast<size_t>(kStatBlocksMax) * 2 * 512 * 4), o_coef = take(3 * 512 * 4);
   const size_t o_gfc = take(static_cast<size_t>(B) * h->emb * 4), o_dP = take(static_cast<size_t>(B) * 2048 * 4);
-  const size_t o_dw = take(static_cast<size_t>(25) * 512 * 256 * 4), o_c1 = take(static_cast<size_t>(1184) * 1600 * 4);
+  const size_t o_dw = take(static_cast<size_t>(25) * 512 * 256 * 4), o_c1 = take(static_cast<size_t>(B) * ((T / 2 + 7) / 8) * 1600 * 4);
   const size_t o_gA = take(max_act), o_gB = take(max_act), o_G = take(max_act), o_gres = take(max_act);
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->base), bytes));
   CUDA_TRY(cudaMemset(c->base, 0, bytes));
@@ -1359,7 +1359,7 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
     dim3 gs(gx, C / 64);
     dsk::bn_stats_partial_kernel<<<gs, 256, 0, s>>>(c->raw[i], M, C, c->partial);
     KERNEL_CHECK();
-    dsk::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], h->w.bn_beta[i],
+    dsk::bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], h->w.bn_beta[i],
                                                            h->w.bn_running_mean[i], h->w.bn_running_var[i], 0.1f, 1e-5f,
                                                            c->mean[i], c->rstd[i], c->scale_t, c->shift_t);
     KERNEL_CHECK();
@@ -1428,7 +1428,7 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
       dsk::bn_bwd_reduce_kernel<false><<<gs, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], c->raw[i], c->mean[i],
                                                           c->rstd[i], M, C, 20.0f, c->partial);
     KERNEL_CHECK();
-    dsk::bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], c->rstd[i], invS,
+    dsk::bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], c->rstd[i], invS,
                                                                g->bn_gamma[i], g->bn_beta[i], c->coef);
     KERNEL_CHECK();
     uint16_t* gres = (i % 3 == 2) ? (uint16_t*)c->gres : nullptr;
@@ -1442,11 +1442,11 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
     KERNEL_CHECK();
     const LayerCfg lc = layer_cfg(i);
     if (i == 0) {
-      const int nblk = 1184;
+      const int nblk = B * ((T / 2 + 7) / 8);
       if (bf) dsk::conv1_wgrad_partial_kernel<true><<<nblk, 256, 0, s>>>((const uint16_t*)c->G, c->x, B, T, c->c1part);
       else dsk::conv1_wgrad_partial_kernel<false><<<nblk, 256, 0, s>>>((const uint16_t*)c->G, c->x, B, T, c->c1part);
       KERNEL_CHECK();
-      dsk::sum_partials_kernel<<<(1600 + 127) / 128, 128, 0, s>>>(c->c1part, nblk, 1600, invS, g->conv_w[0]);
+      dsk::sum_partials_kernel<<<(1600 + 31) / 32, 1024, 0, s>>>(c->c1part, nblk, 1600, invS, g->conv_w[0]);
       KERNEL_CHECK();
     } else {
       const int taps = lc.ksize * lc.ksize;
@@ -1574,7 +1574,7 @@ int32_t dsk_bn_act_train_forward(dsk_handle h, const float* raw, const float* ga
   float *partial = tmp, *sc = tmp + static_cast<size_t>(gx) * 2 * C, *sh = sc + C;
   dsk::bn_stats_partial_kernel<<<dim3(gx, C / 64), 256, 0, s>>>(raw, M, C, partial);
   KERNEL_CHECK();
-  dsk::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, gx, C, M, gamma, beta, running_mean, running_var, 0.1f,
+  dsk::bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(partial, gx, C, M, gamma, beta, running_mean, running_var, 0.1f,
                                                          1e-5f, mean, rstd, sc, sh);
   KERNEL_CHECK();
   dim3 ga(static_cast<unsigned>((M + 63) / 64), C / 64);
@@ -1602,12 +1602,12 @@ int32_t dsk_bn_act_train_backward(dsk_handle h, const void* gy, const void* y, c
   dim3 gs(gx, C / 64), ga(static_cast<unsigned>((M + 63) / 64), C / 64);
   if (h->bf16) {
     dsk::bn_bwd_reduce_kernel<true><<<gs, 256, 0, s>>>((const uint16_t*)gy, (const uint16_t*)y, raw, mean, rstd, M, C, 20.0f, partial);
-    dsk::bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, gx, C, M, gamma, rstd, inv_scale, dgamma, dbeta, coef);
+    dsk::bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(partial, gx, C, M, gamma, rstd, inv_scale, dgamma, dbeta, coef);
     dsk::bn_bwd_apply_kernel<true><<<ga, 256, 0, s>>>((const uint16_t*)gy, (const uint16_t*)y, raw, mean, rstd, coef, (uint16_t*)G,
                                                       (uint16_t*)gres, M, C, 20.0f);
   } else {
     dsk::bn_bwd_reduce_kernel<false><<<gs, 256, 0, s>>>((const uint16_t*)gy, (const uint16_t*)y, raw, mean, rstd, M, C, 20.0f, partial);
-    dsk::bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, gx, C, M, gamma, rstd, inv_scale, dgamma, dbeta, coef);
+    dsk::bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(partial, gx, C, M, gamma, rstd, inv_scale, dgamma, dbeta, coef);
     dsk::bn_bwd_apply_kernel<false><<<ga, 256, 0, s>>>((const uint16_t*)gy, (const uint16_t*)y, raw, mean, rstd, coef, (uint16_t*)G,
                                                        (uint16_t*)gres, M, C, 20.0f);
   }

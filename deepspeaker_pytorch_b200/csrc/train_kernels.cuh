@@ -116,19 +116,58 @@ bn_stats_partial_kernel(const float* __restrict__ raw, long M, int C, float* __r
   }
 }
 
+// Sum of the per-block partials of 32 channels by one 1024-thread block: thread (slice, channel) adds every 32nd
+// partial row in double, the slices are combined in fixed order (deterministic).  A single thread per channel walking
+// all ~1000 rows took ~50 us per launch, a quarter of the training step.
+// Returns the totals to the threads of slice 0 (threadIdx.x < 32); the others get ok == false.
+__device__ __forceinline__ bool bn_partial_totals(const float* __restrict__ partial, int nblk, int C, int c, double& s,
+                                                  double& ss) {
+  __shared__ double red[2][32][33];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  double a = 0.0, b2 = 0.0;
+  if (c < C) {
+    int b = sl;
+    for (; b + 96 < nblk; b += 128) {  // four rows in flight per thread
+      float t0[4], t1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        t0[j] = partial[(static_cast<long>(b + 32 * j) * 2) * C + c];
+        t1[j] = partial[(static_cast<long>(b + 32 * j) * 2 + 1) * C + c];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a += t0[j];
+        b2 += t1[j];
+      }
+    }
+    for (; b < nblk; b += 32) {
+      a += partial[(static_cast<long>(b) * 2) * C + c];
+      b2 += partial[(static_cast<long>(b) * 2 + 1) * C + c];
+    }
+  }
+  red[0][sl][lane] = a;
+  red[1][sl][lane] = b2;
+  __syncthreads();
+  if (sl != 0 || c >= C) return false;
+  s = 0.0;
+  ss = 0.0;
+  for (int i = 0; i < 32; ++i) {
+    s += red[0][i][lane];
+    ss += red[1][i][lane];
+  }
+  return true;
+}
+
 // mean / biased var -> rstd, scale = gamma*rstd, shift = beta - mean*scale; running stats (momentum, unbiased var)
+// grid ceil(C/32), block 1024
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long M,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                    float* __restrict__ scale_out, float* __restrict__ shift_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += partial[(static_cast<long>(b) * 2) * C + c];
-    ss += partial[(static_cast<long>(b) * 2 + 1) * C + c];
-  }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s, ss;
+  if (!bn_partial_totals(partial, nblk, C, c, s, ss)) return;
   const double mean = s / static_cast<double>(M);
   double var = ss / static_cast<double>(M) - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -226,13 +265,9 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
                                        float inv_loss_scale, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef /*[3][C]*/) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += partial[(static_cast<long>(b) * 2) * C + c];
-    ss += partial[(static_cast<long>(b) * 2 + 1) * C + c];
-  }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s, ss;
+  if (!bn_partial_totals(partial, nblk, C, c, s, ss)) return;
   dbeta[c] = static_cast<float>(s) * inv_loss_scale;
   dgamma[c] = static_cast<float>(ss) * inv_loss_scale;
   coef[c] = gamma[c] * rstd[c];
@@ -349,38 +384,65 @@ __global__ void pool_bwd_kernel(const float* __restrict__ dP, uint16_t* __restri
 }
 
 // ---- conv1 weight gradient (Cin = 1): dW[co][r][s] = sum_pix G[pix][co] * x[2h-2+r][2w-2+s] -----------------------
-// grid (nblk), block 256 = 8 warps; warp handles pixels, lane = 2 output channels; 25 taps x 2 accumulators.
-// partial[blk][co][25]; finalized by conv1_wgrad_finalize_kernel.
+// grid B * ceil(hout/8); block 256 = 8 warps.  Same shape as the SIMT conv1 forward: block = 8 output rows of one
+// utterance with their 19 x 68 input patch in shared memory, warp = one output row, lane = 2 output channels with
+// 2 x 25 accumulators in registers; four pixels per iteration share three float4 patch loads per filter row.
+// partial[blk][co][25]; summed by sum_partials_kernel.
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 conv1_wgrad_partial_kernel(const uint16_t* __restrict__ G, const float* __restrict__ x, int B, int T,
                            float* __restrict__ partial) {
+  constexpr int WIN = 64, WOUT = 32, ROWS = 8, PATCH_ROWS = 2 * ROWS + 3, PATCH_W = WIN + 4;
+  __shared__ __align__(16) float patch[PATCH_ROWS][PATCH_W];
   __shared__ float red[64 * 25];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hout = T / 2;
+  const int tiles_h = (hout + ROWS - 1) / ROWS;
+  const int n = blockIdx.x / tiles_h;
+  const int h0 = (blockIdx.x % tiles_h) * ROWS;
+  const float* xin = x + static_cast<long>(n) * T * WIN;
+  {
+    constexpr int NEL = PATCH_ROWS * PATCH_W, NIT = (NEL + 255) / 256;
+    float t[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      const int pr = i / PATCH_W, pc = i % PATCH_W;
+      const int ih = 2 * h0 - 2 + pr, iw = pc - 2;
+      t[j] = (i < NEL && ih >= 0 && ih < T && iw >= 0 && iw < WIN) ? xin[ih * WIN + iw] : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      if (i < NEL) patch[i / PATCH_W][i % PATCH_W] = t[j];
+    }
+  }
   for (int i = threadIdx.x; i < 64 * 25; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  const int hout = T / 2;
-  const long npix = static_cast<long>(B) * hout * 32;
   float a0[25], a1[25];
 #pragma unroll
   for (int t = 0; t < 25; ++t) a0[t] = a1[t] = 0.f;
-  const uint32_t* g32 = reinterpret_cast<const uint32_t*>(G);
-  for (long pix = blockIdx.x * 8L + warp; pix < npix; pix += 8L * gridDim.x) {
-    const int ow = pix & 31;
-    const long r = pix >> 5;
-    const int oh = r % hout;
-    const long n = r / hout;
-    const float2 g = unpack2<BF16>(g32[pix * 32 + lane]);
-    const float* xin = x + n * T * 64;
+  const int oh = h0 + warp;
+  if (oh < hout) {
+    const uint32_t* g32 = reinterpret_cast<const uint32_t*>(G) + ((static_cast<long>(n) * hout + oh) * WOUT) * 32 + lane;
+#pragma unroll 1
+    for (int ow = 0; ow < WOUT; ow += 4) {
+      float2 g[4];
 #pragma unroll
-    for (int rr = 0; rr < 5; ++rr) {
-      const int ih = 2 * oh - 2 + rr;
+      for (int q = 0; q < 4; ++q) g[q] = unpack2<BF16>(g32[(ow + q) * 32]);
 #pragma unroll
-      for (int s = 0; s < 5; ++s) {
-        const int iw = 2 * ow - 2 + s;
-        const float v = (ih >= 0 && ih < T && iw >= 0 && iw < 64) ? xin[ih * 64 + iw] : 0.f;
-        a0[rr * 5 + s] = fmaf(g.x, v, a0[rr * 5 + s]);
-        a1[rr * 5 + s] = fmaf(g.y, v, a1[rr * 5 + s]);
+      for (int r = 0; r < 5; ++r) {
+        const float4* prow = reinterpret_cast<const float4*>(&patch[2 * warp + r][2 * ow]);
+        const float4 v0 = prow[0], v1 = prow[1], v2 = prow[2];
+        const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+        for (int s2 = 0; s2 < 5; ++s2) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            a0[r * 5 + s2] = fmaf(g[q].x, v[2 * q + s2], a0[r * 5 + s2]);
+            a1[r * 5 + s2] = fmaf(g[q].y, v[2 * q + s2], a1[r * 5 + s2]);
+          }
+        }
       }
     }
   }
@@ -398,13 +460,31 @@ conv1_wgrad_partial_kernel(const uint16_t* __restrict__ G, const float* __restri
   for (int i = threadIdx.x; i < 64 * 25; i += blockDim.x) partial[static_cast<long>(blockIdx.x) * 1600 + i] = red[i];
 }
 
+// out[i] = mult * sum_b partial[b][i].  grid ceil(n/32), block 1024: thread (slice, i) adds every 32nd row in double,
+// slices are combined in fixed order.
 __global__ void sum_partials_kernel(const float* __restrict__ partial, int nblk, int n, float mult,
                                     float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  __shared__ double red[32][33];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   double t = 0.0;
-  for (int b = 0; b < nblk; ++b) t += partial[static_cast<long>(b) * n + i];
-  out[i] = static_cast<float>(t) * mult;
+  if (i < n) {
+    int b = sl;
+    for (; b + 96 < nblk; b += 128) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = partial[static_cast<long>(b + 32 * j) * n + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t += v[j];
+    }
+    for (; b < nblk; b += 32) t += partial[static_cast<long>(b) * n + i];
+  }
+  red[sl][lane] = t;
+  __syncthreads();
+  if (sl != 0 || i >= n) return;
+  double tot = 0.0;
+  for (int k = 0; k < 32; ++k) tot += red[k][lane];
+  out[i] = static_cast<float>(tot) * mult;
 }
 
 // dW fp32 [tap][co][ci] (accumulated by the wgrad GEMM) -> OIHW [co][ci][tap] scaled by mult.
