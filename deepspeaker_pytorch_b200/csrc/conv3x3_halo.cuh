@@ -22,7 +22,7 @@ namespace dsk {
 // (r&1, s&1) at a fixed shift ((r-2)>>1, (s-2)>>1) of the output position: one halo box per (64-channel chunk, plane)
 // serves all taps of that plane.  The K loop is table driven: a sequence of weight BOXES (<= 3 taps each, packed
 // consecutively in plane-major tap order), each tap with its own row shift into the current plane's halo tile.
-constexpr int kHaloMaxBoxes = 12;
+constexpr int kHaloMaxBoxes = 25;
 constexpr int kHaloMaxStages = 4;
 
 struct HaloParams {
@@ -51,8 +51,11 @@ struct HaloParams {
   int out_C;
   int flags;              // CONV_RESIDUAL | CONV_CLIP
   float clip_hi;
-  const float* scale;
-  const float* bias;
+  // folded eval-BN affine of the layer's output channels, carried in the kernel parameters: the epilogue reads it
+  // through the constant cache (warp-uniform addresses) instead of spending shared-memory bandwidth, which is the
+  // resource the MMA operand fetch already saturates
+  float scale_c[512];
+  float bias_c[512];
   int plain3x3;           // MMA issuer plan: 1 = 3x3 (HaloPlan<1>), 2 = planar 5x5 s2 (HaloPlan<2>), 0 = walk the tables
   int late_trigger;       // release the dependent kernel when this CTA starts its last tile instead of at entry
   int b_resident;         // all weight boxes of a CTA's channel tile fit the B ring: load once
@@ -69,30 +72,32 @@ struct HaloParams {
 // Compile-time K-loop plans for the MMA issuer (the producer still walks the runtime tables, which say the same).
 // KIND 1: 3x3, one plane, boxes = filter rows.  KIND 2: planar 5x5 s2, packed tap n = 3*box + t, planes start at
 // packed taps 0 / 9 / 15 / 21 and have 3x3, 3x2, 2x3, 2x2 taps; tap (i, j) of a plane reads halo row i*(W+1) + j.
-template <int KIND>
+template <int KIND, int TPB>  // TPB = taps per weight box (3, or 1 for the 256-channel tile)
 struct HaloPlan {
-  static constexpr int kBoxes = KIND == 1 ? 3 : 9;
+  static constexpr int kTaps = KIND == 1 ? 9 : 25;
+  static constexpr int kBoxes = (kTaps + TPB - 1) / TPB;  // plane starts 0/9/15/21 are multiples of 3: boxes never straddle planes
   __host__ __device__ static constexpr int plane_of(int n) { return KIND == 1 ? 0 : (n < 9 ? 0 : n < 15 ? 1 : n < 21 ? 2 : 3); }
   __host__ __device__ static constexpr int plane_start(int pl) { return pl == 0 ? 0 : pl == 1 ? 9 : pl == 2 ? 15 : 21; }
+  __host__ __device__ static constexpr int plane_end(int pl) { return KIND == 1 ? 9 : (pl == 0 ? 9 : pl == 1 ? 15 : pl == 2 ? 21 : 25); }
   __host__ __device__ static constexpr int cols(int pl) { return (KIND == 2 && (pl & 1)) ? 2 : 3; }
-  __host__ __device__ static constexpr int ntaps(int b) { return (KIND == 2 && b == 8) ? 1 : 3; }
-  __host__ __device__ static constexpr bool first(int b) { return KIND == 1 ? b == 0 : (b == 0 || b == 3 || b == 5 || b == 7); }
-  __host__ __device__ static constexpr bool last(int b) { return KIND == 1 ? b == 2 : (b == 2 || b == 4 || b == 6 || b == 8); }
+  __host__ __device__ static constexpr int ntaps(int b) { return kTaps - TPB * b < TPB ? kTaps - TPB * b : TPB; }
+  __host__ __device__ static constexpr bool first(int b) { return TPB * b == plane_start(plane_of(TPB * b)); }
+  __host__ __device__ static constexpr bool last(int b) { return TPB * b + ntaps(b) == plane_end(plane_of(TPB * b)); }
   __host__ __device__ static constexpr int row_i(int b, int t) {
-    return (3 * b + t - plane_start(plane_of(3 * b + t))) / cols(plane_of(3 * b + t));
+    return (TPB * b + t - plane_start(plane_of(TPB * b + t))) / cols(plane_of(TPB * b + t));
   }
   __host__ __device__ static constexpr int col_j(int b, int t) {
-    return (3 * b + t - plane_start(plane_of(3 * b + t))) % cols(plane_of(3 * b + t));
+    return (TPB * b + t - plane_start(plane_of(TPB * b + t))) % cols(plane_of(TPB * b + t));
   }
 };
 
 template <int N_TILE>
 struct HaloSmem {
-  static constexpr int kBStageBytes = 3 * N_TILE * 128;      // one weight box: 3 taps
-  static constexpr int kScaleBiasBytes = 2 * 512 * 4;
-  static constexpr int kAccStages = 4;                       // TMEM accumulators: 4 x N_TILE <= 512 columns
+  static constexpr int kTapsPerBox = N_TILE == 256 ? 1 : 3;  // weight box: 3 taps (48 KB at 128 channels), 1 tap at 256
+  static constexpr int kBStageBytes = kTapsPerBox * N_TILE * 128;
+  static constexpr int kAccStages = N_TILE == 256 ? 2 : 4;   // TMEM accumulators: kAccStages x N_TILE <= 512 columns
   static constexpr int kRowDstBytes = 2 * 128 * 8;                  // planar output: per-row destination, two tiles
-  static constexpr int kFixedBytes = kScaleBiasBytes + kRowDstBytes + 512 + 1024;  // + barriers + alignment slack
+  static constexpr int kFixedBytes = kRowDstBytes + 512 + 1024;  // + barriers + alignment slack
   static int total(int a_stage_bytes, int a_stages, int b_stages, int stg_bufs, int res_bufs) {
     return a_stages * a_stage_bytes + b_stages * kBStageBytes + (stg_bufs + res_bufs) * kATileBytes + kFixedBytes;
   }
@@ -134,9 +139,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   uint8_t* smem_b = smem_a + kAStages * p.a_stage_bytes;
   uint8_t* smem_stg = smem_b + kBStages * S::kBStageBytes;
   uint8_t* smem_res = smem_stg + p.stg_bufs * kATileBytes;
-  float* smem_scale = reinterpret_cast<float*>(smem_res + p.res_bufs * kATileBytes);
-  float* smem_bias = smem_scale + 512;
-  uint16_t** row_dst = reinterpret_cast<uint16_t**>(reinterpret_cast<uint8_t*>(smem_scale) + S::kScaleBiasBytes);
+  uint16_t** row_dst = reinterpret_cast<uint16_t**>(smem_res + p.res_bufs * kATileBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(row_dst) + S::kRowDstBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kHaloMaxStages;
@@ -221,10 +224,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   if (warp == 2) {
     tmem_alloc(tmem_ptr_smem, kTmemCols);
     tmem_relinquish();
-  }
-  for (int i = threadIdx.x; i < p.cout && i < 512; i += blockDim.x) {
-    smem_scale[i] = p.scale ? p.scale[i] : 1.0f;
-    smem_bias[i] = p.bias ? p.bias[i] : 0.0f;
   }
   tc_fence_before();
   __syncthreads();
@@ -374,8 +373,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
             }
           }
         };
-        if (p.plain3x3 == 1) issue_chunks(HaloPlan<1>{});
-        else issue_chunks(HaloPlan<2>{});
+        if (p.plain3x3 == 1) issue_chunks(HaloPlan<1, S::kTapsPerBox>{});
+        else issue_chunks(HaloPlan<2, S::kTapsPerBox>{});
       } else
       for (int ch = 0; ch < p.chunks; ++ch) {
         uint64_t da0 = 0;
@@ -511,19 +510,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         if (has_res) mbar_wait(&res_full[rb], rph);
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 4);
         const uint8_t* res_row = smem_res + rb * kATileBytes + row * 128;
-        const float* sc = smem_scale + c0 + j * 64 + half * 32;
-        const float* bi = smem_bias + c0 + j * 64 + half * 32;
+        const int cbase = c0 + j * 64 + half * 32;
         uint8_t* my_row = stg + row * 128;
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
           float f[8];
-          // per-channel scale / bias: four broadcast 16-byte shared-memory loads for 8 channels
-          const float4 s0 = *reinterpret_cast<const float4*>(sc + qq * 8);
-          const float4 s1 = *reinterpret_cast<const float4*>(sc + qq * 8 + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(bi + qq * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(bi + qq * 8 + 4);
-          const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          const float biv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          // per-channel scale / bias from the parameter (constant) bank: the index is warp-uniform
+          float scv[8], biv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            scv[e] = p.scale_c[cbase + qq * 8 + e];
+            biv[e] = p.bias_c[cbase + qq * 8 + e];
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[qq * 8 + e]), scv[e], biv[e]);
           const int chunk16 = ((half * 4 + qq) ^ (row & 7)) << 4;  // 16-byte slot inside the swizzled 128-byte row

@@ -169,6 +169,8 @@ struct dsk_handle_s {
   float* conv1_w = nullptr;           // fp32 [64][25]
   uint16_t* conv1_img = nullptr;      // pre-swizzled hi/lo split operand image of conv1_umma_kernel (16 KB)
   float* scale[DSK_NUM_CONV] = {};    // folded eval BN
+  std::vector<float> scale_host[DSK_NUM_CONV], bias_host[DSK_NUM_CONV];  // host copies for the halo kernels' parameters
+  bool host_affine_valid = false;
   float* bias[DSK_NUM_CONV] = {};
   float* fc_wq = nullptr;             // fp32 [E][w*512+c]
   const float* fc_b = nullptr;        // borrowed (valid until next load_weights)
@@ -224,13 +226,15 @@ struct dsk_handle_s {
   int ap_N = 0, ap_D = 0;
   uint8_t* ap_buf = nullptr;
   std::vector<ConvLaunch> ap_gemm;
+  bool n256 = false;           // DSK_N256=1: 256-channel tiles for layers with >= n256_min_tiles such tiles
+  int n256_min_tiles = 80;
   bool use_graph = true;       // DSK_GRAPH=0: always launch the forward kernel by kernel
   bool conv1_pdl = true;       // debug knob DSK_CONV1_PDL=0: launch conv1 with plain stream serialisation
   bool late_trigger = false;   // debug knob DSK_LATE_TRIGGER=1: halo kernels release their dependents at the last tile
   bool planar_s2 = true;       // eval forward: run the 5x5 s2 convs in the halo kernel's parity-planar form (DSK_PLANAR_S2=0: generic kernel)
   long long* trace = nullptr;  // debug: device buffer [3][512] for conv3x3_halo_kernel clock stamps
   // optional per-launch timing (dsk_set_profiling): events recorded around every kernel of a forward
-  bool profiling = false;
+  int profiling = 0;  // 0 off, 1 per launch, 2 per section
   std::vector<cudaEvent_t> events;
   int n_marks = 0;
 };
@@ -605,11 +609,21 @@ void planar_tap_order(int* perm /*[25]*/) {
         for (int s = pw; s < 5; s += 2) perm[n++] = r * 5 + s;
 }
 
+// device per-channel affine -> host vectors (plan build / single-op entry points only: synchronises the device)
+int fetch_affine(const float* scale_d, const float* bias_d, int n, std::vector<float>* sc, std::vector<float>* bi) {
+  sc->assign(n, 1.0f);
+  bi->assign(n, 0.0f);
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (scale_d) CUDA_TRY(cudaMemcpy(sc->data(), scale_d, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (bias_d) CUDA_TRY(cudaMemcpy(bi->data(), bias_d, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return DSK_OK;
+}
+
 // Halo-reuse conv on the padded layout (conv3x3_halo.cuh).  ksize 3 (stride 1, C -> C, input = standard padded
 // layout of the same geometry) or ksize 5 (stride 2, input = parity-planar padded layout at the OUTPUT geometry).
 // (N, H, W) is the OUTPUT geometry.  out_planar: write the output parity-planar (it feeds a stride-2 conv).
-int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void* wpk, const float* scale,
-               const float* bias, const void* res, void* out, int N, int H, int W, int cin, int cout, int ksize,
+int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void* wpk, const float* scale_host,
+               const float* bias_host, const void* res, void* out, int N, int H, int W, int cin, int cout, int ksize,
                int flags, float clip_hi, int out_planar) {
   if (cin % 64 || cin < 64 || cout % 64 || cout < 64 || cout > 512)
     return fail(DSK_ERR_INVALID, "halo conv: channel counts must be multiples of 64 (got %d -> %d)", cin, cout);
@@ -624,15 +638,21 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   p.q_begin = W + 1;
   const long q_end = static_cast<long>(N) * (H + 1) * (W + 1);   // one past the last real pixel position
   p.tiles_m = static_cast<int>((q_end - p.q_begin + 127) / 128);
-  const int n_tile = cout == 64 ? 64 : 128;
+  // 256-channel tiles halve the weight-operand shared-memory traffic per FLOP (the binding resource)
+  // but halve the tile count: used when the layer still has enough tiles to spread over the SMs
+  const int tiles_m_ = static_cast<int>((q_end - p.q_begin + 127) / 128);
+  const int n_tile = cout == 64 ? 64 : (h->n256 && cout % 256 == 0 && tiles_m_ * (cout / 256) >= h->n256_min_tiles) ? 256 : 128;
+  const int tpb = n_tile == 256 ? 1 : 3;
   L->n_tile = n_tile;
   p.tiles_c = cout / n_tile;
   p.chunks = cin / 64;
   p.cout = cout;
   p.flags = flags;
   p.clip_hi = clip_hi;
-  p.scale = scale;
-  p.bias = bias;
+  for (int i = 0; i < cout; ++i) {
+    p.scale_c[i] = scale_host ? scale_host[i] : 1.0f;
+    p.bias_c[i] = bias_host ? bias_host[i] : 0.0f;
+  }
   p.trace = h->trace;
   p.late_trigger = h->late_trigger ? 1 : 0;
   p.pitch_magic = static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(W + 1)) + 1u;
@@ -641,15 +661,18 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   int ntaps_total;
   if (ksize == 3) {
     ntaps_total = 9;
-    p.nboxes = 3;
+    p.nboxes = 9 / tpb;
     p.plane_positions = 0;
-    for (int r = 0; r < 3; ++r) {
-      p.box_plane[r] = 0;
-      p.box_first[r] = r == 0;
-      p.box_last[r] = r == 2;
-      p.box_ntaps[r] = 3;
-      p.box_wtap[r] = (int16_t)(3 * r);
-      for (int s2 = 0; s2 < 3; ++s2) p.tap_shift[r][s2] = (int16_t)(r * (W + 1) + s2);
+    for (int b = 0; b < p.nboxes; ++b) {
+      p.box_plane[b] = 0;
+      p.box_first[b] = b == 0;
+      p.box_last[b] = b == p.nboxes - 1;
+      p.box_ntaps[b] = (int8_t)tpb;
+      p.box_wtap[b] = (int16_t)(tpb * b);
+      for (int t = 0; t < tpb; ++t) {
+        const int tap = tpb * b + t;
+        p.tap_shift[b][t] = (int16_t)((tap / 3) * (W + 1) + tap % 3);
+      }
     }
   } else {
     ntaps_total = 25;
@@ -660,11 +683,11 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
     for (int pl = 0; pl < 4; ++pl) {
       const int ph = pl >> 1, pw = pl & 1;
       const int cnt = (ph ? 2 : 3) * (pw ? 2 : 3);
-      for (int t0 = 0; t0 < cnt; t0 += 3, ++nb) {
+      for (int t0 = 0; t0 < cnt; t0 += tpb, ++nb) {
         p.box_plane[nb] = (int8_t)pl;
         p.box_first[nb] = t0 == 0;
-        p.box_last[nb] = t0 + 3 >= cnt;
-        p.box_ntaps[nb] = (int8_t)(cnt - t0 < 3 ? cnt - t0 : 3);
+        p.box_last[nb] = t0 + tpb >= cnt;
+        p.box_ntaps[nb] = (int8_t)(cnt - t0 < tpb ? cnt - t0 : tpb);
         p.box_wtap[nb] = (int16_t)(slot + t0);
         for (int t = 0; t < p.box_ntaps[nb]; ++t) {
           const int rs = perm[slot + t0 + t];
@@ -674,7 +697,7 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
       }
       slot += cnt;
     }
-    p.nboxes = nb;  // 3 + 2 + 2 + 2 = 9
+    p.nboxes = nb;  // 3 + 2 + 2 + 2 = 9 three-tap boxes, or 25 single taps
   }
   // all weight boxes of a CTA fit the B ring and every tile of the CTA uses the same ones: load them once
   p.plain3x3 = ksize == 3 ? 1 : 2;
@@ -692,8 +715,8 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
     const int halo_rows = 128 + 2 * W + 4;
     p.a_stage_bytes = (halo_rows * 128 + 1023) / 1024 * 1024;
     const bool has_res = (flags & dsk::CONV_RESIDUAL) != 0;
-    const int b_bytes = 3 * n_tile * 128;
-    const int fixed = n_tile == 64 ? dsk::HaloSmem<64>::kFixedBytes : dsk::HaloSmem<128>::kFixedBytes;
+    const int b_bytes = tpb * n_tile * 128;
+    const int fixed = dsk::HaloSmem<128>::kFixedBytes;  // the same for every tile width
     const int limit = 227 * 1024;
     p.a_stages = n_tile == 64 ? 3 : 2;
     p.stg_bufs = 2;
@@ -721,7 +744,7 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   if (rc) return rc;
   uint64_t wd[3] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)ntaps_total};
   uint64_t ws[2] = {2ull * cin, 2ull * cin * cout};
-  uint32_t wb[3] = {64, (uint32_t)n_tile, 3};
+  uint32_t wb[3] = {64, (uint32_t)n_tile, (uint32_t)tpb};
   rc = make_tmap(&L->tmW, bf, wpk, 3, wd, ws, wb);
   if (rc) return rc;
   // output / residual: standard padded layout of the output geometry (with a planar output the map is unused but
@@ -748,8 +771,9 @@ int launch_halo_t(const HaloLaunch& L, cudaStream_t s) {
 }
 
 int launch_halo(const dsk_handle_s* h, const HaloLaunch& L, cudaStream_t s) {
-  if (h->bf16) return L.n_tile == 64 ? launch_halo_t<64, true>(L, s) : launch_halo_t<128, true>(L, s);
-  return L.n_tile == 64 ? launch_halo_t<64, false>(L, s) : launch_halo_t<128, false>(L, s);
+  if (h->bf16)
+    return L.n_tile == 64 ? launch_halo_t<64, true>(L, s) : L.n_tile == 128 ? launch_halo_t<128, true>(L, s) : launch_halo_t<256, true>(L, s);
+  return L.n_tile == 64 ? launch_halo_t<64, false>(L, s) : L.n_tile == 128 ? launch_halo_t<128, false>(L, s) : launch_halo_t<256, false>(L, s);
 }
 
 int check_handle(dsk_handle h) {
@@ -825,6 +849,13 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
   pl.fc_part = reinterpret_cast<float*>(base + off_fc_part);
   pl.conv.resize(DSK_NUM_CONV);
   pl.halo.resize(DSK_NUM_CONV);
+  if (!h->host_affine_valid) {  // once per weight load: host copy of the folded BN affine for the kernel parameters
+    for (int i = 1; i < DSK_NUM_CONV; ++i) {
+      int rc2 = fetch_affine(h->scale[i], h->bias[i], layer_cfg(i).cout, &h->scale_host[i], &h->bias_host[i]);
+      if (rc2) return rc2;
+    }
+    h->host_affine_valid = true;
+  }
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
     const LayerCfg c = layer_cfg(i);
     int Hi, Wi, Ci;
@@ -834,7 +865,7 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
     act_shape(i, T, Ho, Wo, Co);
     int rc;
     if (k == 0 && h->planar_s2) {
-      rc = build_halo(h, &pl.halo[i], pl.act[i - 1], h->wpk_planar[i], h->scale[i], h->bias[i], nullptr, pl.act[i], B, Ho, Wo,
+      rc = build_halo(h, &pl.halo[i], pl.act[i - 1], h->wpk_planar[i], h->scale_host[i].data(), h->bias_host[i].data(), nullptr, pl.act[i], B, Ho, Wo,
                       c.cin, c.cout, 5, dsk::CONV_CLIP, 20.0f, 0);
     } else if (k == 0) {
       // default: the generic tap kernel reads the padded input through its parity view (measured 4 % faster end to end
@@ -845,7 +876,7 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
       const void* res = (k == 2) ? pl.act[i - 2] : nullptr;  // block output adds the block input
       const int flags = dsk::CONV_CLIP | (k == 2 ? dsk::CONV_RESIDUAL : 0);
       const int out_planar = (h->planar_s2 && k == 2 && i < DSK_NUM_CONV - 1) ? 1 : 0;
-      rc = build_halo(h, &pl.halo[i], pl.act[i - 1], h->wpk[i], h->scale[i], h->bias[i], res, pl.act[i], B, Ho, Wo, c.cin,
+      rc = build_halo(h, &pl.halo[i], pl.act[i - 1], h->wpk[i], h->scale_host[i].data(), h->bias_host[i].data(), res, pl.act[i], B, Ho, Wo, c.cin,
                       c.cout, 3, flags, 20.0f, out_planar);
     }
     if (rc) return rc;
@@ -881,6 +912,10 @@ int32_t dsk_create(dsk_handle* out, int32_t device, int32_t operand) {
   {
     const char* e = getenv("DSK_PLANAR_S2");  // default on; DSK_PLANAR_S2=0 runs the 5x5 s2 convs in the generic tap kernel
     h->planar_s2 = !(e && e[0] == '0');
+    e = getenv("DSK_N256");
+    h->n256 = e && e[0] == '1';
+    e = getenv("DSK_N256_MIN_TILES");
+    if (e) h->n256_min_tiles = atoi(e);
     e = getenv("DSK_GRAPH");
     h->use_graph = !(e && e[0] == '0');
     e = getenv("DSK_CONV1_PDL");
@@ -937,7 +972,9 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
     return fail(DSK_ERR_INVALID, "dsk_load_weights: embedding_size must be a positive multiple of 64");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (h->weights_loaded && h->emb != w->embedding_size) return fail(DSK_ERR_INVALID, "embedding_size changed");
-  for (auto& kv : h->plans) kv.second.reset_graph();  // captured graphs hold borrowed parameter pointers (fc bias)
+  // eval plans carry the folded BN affine in their kernel parameters (and their graphs borrowed parameter pointers)
+  h->plans.clear();
+  h->host_affine_valid = false;
   h->emb = w->embedding_size;
   for (int i = 0; i < DSK_NUM_CONV; ++i) {
     const LayerCfg c = layer_cfg(i);
@@ -1015,8 +1052,10 @@ namespace {
 int enqueue_forward(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B, int T, float* emb, cudaStream_t s) {
   int rc = 0;
   h->n_marks = 0;
-  auto mark = [&]() {
-    if (!h->profiling) return;
+  // profiling level 1: an event after every launch; level 2: only at the section boundaries (conv1 | the 11
+  // tensor-core convs | tail), so the conv chain runs back to back exactly as in production
+  auto mark = [&](bool boundary = false) {
+    if (!h->profiling || (h->profiling == 2 && !boundary)) return;
     if (h->n_marks >= static_cast<int>(h->events.size())) {
       cudaEvent_t e;
       cudaEventCreate(&e);
@@ -1024,7 +1063,7 @@ int enqueue_forward(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B,
     }
     cudaEventRecord(h->events[h->n_marks++], s);
   };
-  mark();
+  mark(true);
   // conv1 (+bn1 +clip)
   {
     const int blocks = B * (T / 2 / 4);  // 4 output rows x 32 pixels per CTA
@@ -1034,12 +1073,12 @@ int enqueue_forward(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B,
     else
       CUDA_TRY(launch_opt(h->conv1_pdl, dsk::conv1_umma_kernel<false>, dim3(blocks), dim3(128), 0, s, x, (const uint4*)h->conv1_img,
                           (const float*)h->scale[0], (const float*)h->bias[0], (uint16_t*)pl->act[0], T, 20.0f));
-    mark();
+    mark(true);
   }
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
     rc = (i % 3 == 0 && !h->planar_s2) ? launch_conv(h, pl->conv[i], s) : launch_halo(h, pl->halo[i], s);
     if (rc) return rc;
-    mark();
+    mark(i == DSK_NUM_CONV - 1);
   }
   // tail
   {
@@ -1063,7 +1102,7 @@ int enqueue_forward(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B,
     mark();
     CUDA_TRY(launch_pdl(dsk::l2norm_kernel, dim3(B), dim3(512), 0, s, (const float*)pl->fc_part, (int)dsk::kFcSplit,
                         (const float*)h->fc_b, pl->fc_out, emb, (float*)nullptr, B, h->emb, 10.0f));
-    mark();
+    mark(true);
   }
   return DSK_OK;
 }
@@ -1194,7 +1233,7 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
 
 int32_t dsk_set_profiling(dsk_handle h, int32_t enable) {
   if (!h) return fail(DSK_ERR_INVALID, "null handle");
-  h->profiling = enable != 0;
+  h->profiling = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   h->n_marks = 0;
   return DSK_OK;
 }
@@ -1624,7 +1663,11 @@ int32_t dsk_conv3x3_padded(dsk_handle h, const void* in, const void* w_packed, c
   if (!in || !w_packed || !out) return fail(DSK_ERR_INVALID, "dsk_conv3x3_padded: null pointer");
   if ((flags & dsk::CONV_RESIDUAL) && !res) return fail(DSK_ERR_INVALID, "dsk_conv3x3_padded: residual flag without res");
   HaloLaunch L;
-  rc = build_halo(h, &L, in, w_packed, scale, bias, res, out, N, H, W, C, C, 3, flags, clip_hi, out_planar);
+  std::vector<float> sc_h, bi_h;
+  rc = fetch_affine(scale, bias, C, &sc_h, &bi_h);
+  if (rc) return rc;
+  rc = build_halo(h, &L, in, w_packed, scale ? sc_h.data() : nullptr, bias ? bi_h.data() : nullptr, res, out, N, H, W, C, C, 3,
+                  flags, clip_hi, out_planar);
   if (rc) return rc;
   return launch_halo(h, L, static_cast<cudaStream_t>(stream));
 }
@@ -1651,7 +1694,11 @@ int32_t dsk_conv5x5s2_planar(dsk_handle h, const void* in_planar, const float* w
   KERNEL_CHECK();
   CUDA_TRY(cudaStreamSynchronize(s));  // perm[] is a stack array
   HaloLaunch L;
-  rc = build_halo(h, &L, in_planar, wpk, scale, bias, nullptr, out, N, Hout, Wout, cin, cout, 5, flags, clip_hi, 0);
+  std::vector<float> sc_h, bi_h;
+  rc = fetch_affine(scale, bias, cout, &sc_h, &bi_h);
+  if (!rc)
+    rc = build_halo(h, &L, in_planar, wpk, scale ? sc_h.data() : nullptr, bias ? bi_h.data() : nullptr, nullptr, out, N, Hout,
+                    Wout, cin, cout, 5, flags, clip_hi, 0);
   if (!rc) rc = launch_halo(h, L, s);
   CUDA_TRY(cudaFreeAsync(wpk, s));
   CUDA_TRY(cudaFreeAsync(perm_d, s));
