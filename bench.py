@@ -532,7 +532,7 @@ def main():
         "host_enqueue_ms_per_step": host_ms_value,
         "e2e": {"value": e2e_value, "unit": "emb/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * 512 * 4,
                 "ms_per_step": ms_e2e / K, "host_enqueue_ms_per_step": host_ms_e2e, "api": "EmbeddingPipeline.embed(pinned host batch) -> pinned host embeddings: H2D, "
-                                                  "the engine forward (2 lanes) and D2H on their own streams"},
+                                                  f"the engine forward ({args.lanes} lanes, one CUDA graph per forward) and D2H on their own streams"},
         "gpu_launches": 15 * K,
         "roofline": roofline,
         "tflops_whole_step": B * FLOP_PER_EMB / (ms / K * 1e-3) / 1e12,

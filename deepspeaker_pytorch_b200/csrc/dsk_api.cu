@@ -161,6 +161,9 @@ struct dsk_handle_s {
   int num_sms = 148;
   bool weights_loaded = false;
   int emb = 512;
+  long weights_epoch = 0;             // bumped by every dsk_load_weights
+  dsk_handle_s* src = nullptr;        // dsk_share_weights: the handle whose packed weights this one borrows
+  long seen_epoch = -1;
   // packed parameters
   void* wpk[DSK_NUM_CONV] = {};       // 16-bit [tap][cout][cin]   (conv1: nullptr)
   void* wpk_dgrad[DSK_NUM_CONV] = {}; // 16-bit [tap][cin][cout] for the data gradient (rotated for stride 1)
@@ -940,17 +943,19 @@ int32_t dsk_create(dsk_handle* out, int32_t device, int32_t operand) {
 int32_t dsk_destroy(dsk_handle h) {
   if (!h) return DSK_OK;
   cudaSetDevice(h->device);
-  for (int i = 0; i < DSK_NUM_CONV; ++i) {
-    cudaFree(h->wpk[i]);
-    cudaFree(h->wpk_dgrad[i]);
-    cudaFree(h->wpk_planar[i]);
-    cudaFree(h->scale[i]);
-    cudaFree(h->bias[i]);
+  if (!h->src) {  // a borrower's parameter pointers belong to its source
+    for (int i = 0; i < DSK_NUM_CONV; ++i) {
+      cudaFree(h->wpk[i]);
+      cudaFree(h->wpk_dgrad[i]);
+      cudaFree(h->wpk_planar[i]);
+      cudaFree(h->scale[i]);
+      cudaFree(h->bias[i]);
+    }
+    cudaFree(h->conv1_w);
+    cudaFree(h->conv1_img);
+    cudaFree(h->planar_perm);
+    cudaFree(h->fc_wq);
   }
-  cudaFree(h->conv1_w);
-  cudaFree(h->conv1_img);
-  cudaFree(h->planar_perm);
-  cudaFree(h->fc_wq);
   cudaFree(h->ws);
   cudaFree(h->ap_buf);
   cudaFree(h->ones);
@@ -971,7 +976,9 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
   if (w->embedding_size <= 0 || w->embedding_size % 64)
     return fail(DSK_ERR_INVALID, "dsk_load_weights: embedding_size must be a positive multiple of 64");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->src) return fail(DSK_ERR_STATE, "dsk_load_weights: this handle borrows its weights (dsk_share_weights)");
   if (h->weights_loaded && h->emb != w->embedding_size) return fail(DSK_ERR_INVALID, "embedding_size changed");
+  ++h->weights_epoch;
   // eval plans carry the folded BN affine in their kernel parameters (and their graphs borrowed parameter pointers)
   h->plans.clear();
   h->host_affine_valid = false;
@@ -1046,7 +1053,45 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
   return DSK_OK;
 }
 
+int32_t dsk_share_weights(dsk_handle h, dsk_handle src) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!src || src == h || src->src) return fail(DSK_ERR_INVALID, "dsk_share_weights: bad source handle");
+  if (h->weights_loaded && !h->src) return fail(DSK_ERR_STATE, "dsk_share_weights: the handle already owns weights");
+  if (h->device != src->device || h->bf16 != src->bf16)
+    return fail(DSK_ERR_INVALID, "dsk_share_weights: device / operand type differ from the source");
+  h->src = src;
+  h->seen_epoch = -1;
+  return DSK_OK;
+}
+
 namespace {
+
+// a borrowing handle picks up the source's current parameter pointers; its plans (which bake the folded BN affine
+// into kernel parameters) are rebuilt.  Plan building synchronises the device (fetch_affine), which also orders this
+// handle's stream after the source's repack kernels.
+void adopt_shared_weights(dsk_handle h) {
+  dsk_handle_s* s = h->src;
+  if (!s || h->seen_epoch == s->weights_epoch) return;
+  for (int i = 0; i < DSK_NUM_CONV; ++i) {
+    h->wpk[i] = s->wpk[i];
+    h->wpk_dgrad[i] = s->wpk_dgrad[i];
+    h->wpk_planar[i] = s->wpk_planar[i];
+    h->scale[i] = s->scale[i];
+    h->bias[i] = s->bias[i];
+  }
+  h->conv1_w = s->conv1_w;
+  h->conv1_img = s->conv1_img;
+  h->planar_perm = s->planar_perm;
+  h->fc_wq = s->fc_wq;
+  h->fc_b = s->fc_b;
+  h->w = s->w;
+  h->emb = s->emb;
+  h->weights_loaded = s->weights_loaded;
+  h->plans.clear();
+  h->host_affine_valid = false;
+  h->seen_epoch = s->weights_epoch;
+}
 
 // the 15 launches of one eval forward on stream s
 int enqueue_forward(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B, int T, float* emb, cudaStream_t s) {
@@ -1206,6 +1251,7 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
                            void* stream) {
   int rc = check_handle(h);
   if (rc) return rc;
+  adopt_shared_weights(h);
   if (!h->weights_loaded) return fail(DSK_ERR_STATE, "dsk_rescnn_forward: call dsk_load_weights first");
   if (!x || !emb || B <= 0) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: bad arguments");
   if (T < 16 || T % 16) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: T must be a positive multiple of 16 (got %d)", T);

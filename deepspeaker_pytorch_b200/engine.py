@@ -31,7 +31,9 @@ def _f32c(t):
 
 
 class Engine:
-    def __init__(self, module, device, operand_dtype):
+    def __init__(self, module, device, operand_dtype, share_from=None):
+        """``share_from``: another Engine of the same module whose packed weights this one borrows (inference lanes of
+        ``EmbeddingPipeline``: one weight image in L2 for all forwards in flight)."""
         if device.type != "cuda":
             raise RuntimeError("the B200 engine runs on CUDA devices only")
         self.lib = L.load()
@@ -44,6 +46,9 @@ class Engine:
         self._versions = None
         self._wstruct = None
         self.train_calls = 0  # train-mode forwards update BN running stats through raw pointers
+        self.share_from = share_from
+        if share_from is not None:
+            L.check(self.lib.dsk_share_weights(self.handle, share_from.handle), "dsk_share_weights")
 
     def set_loss_scale(self, scale: float):
         """fp16 gradient scale used inside the backward (0 = automatic, see include/dsk.h)."""
@@ -72,6 +77,11 @@ class Engine:
 
     def sync_weights(self, eval_mode=True):
         """Repack/fold when any parameter (or, in eval, BN buffer) changed since the last call."""
+        if self.share_from is not None:
+            if not eval_mode:
+                raise RuntimeError("an engine that borrows its weights is inference-only")
+            self.share_from.sync_weights(True)
+            return
         vs = self._param_versions(eval_mode)
         if vs == self._versions:
             return

@@ -79,6 +79,11 @@ int32_t dsk_destroy(dsk_handle h);
 /* Repack conv weights to [tap][cout][cin] 16-bit, fold eval BatchNorm to scale/bias, reorder fc.
  * Must be called after every parameter update (the Python shim tracks parameter versions). */
 int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream);
+/* Serving with several forwards in flight (one handle + activation workspace per compute stream): `h` borrows the
+ * packed weights / folded BN of `src` instead of holding its own copy, so all lanes read one 21 MB weight image (it
+ * has to stay L2-resident: the convs re-read it per tile).  `h` follows later dsk_load_weights(src) calls at its next
+ * forward; it is inference-only, must not be given weights of its own, and `src` must outlive it. */
+int32_t dsk_share_weights(dsk_handle h, dsk_handle src);
 
 /* DeepSpeakerModel.forward (/root/reference/model.py:185-218), BN in eval mode
  * (train_triplet.py:332,347): x (B,1,T,64) fp32 contiguous -> emb (B,E) fp32 with ||emb||=10.
@@ -105,9 +110,10 @@ int32_t dsk_train_ctx_release(dsk_handle h, dsk_train_ctx ctx);
  * out of every parameter gradient (0 = automatic: 2^(9+floor(log2 B)) capped at 2^16 for fp16, 1 for bf16). */
 int32_t dsk_set_loss_scale(dsk_handle h, float scale);
 
-/* Per-launch device timing of the next dsk_rescnn_forward calls: when enabled, CUDA events are recorded on
- * `stream` around every kernel of the forward (order: conv1, the 11 tensor-core convs in network order,
- * pool, fc, l2norm).  dsk_get_launch_times waits for the last profiled forward (the only call in this
+/* Device timing of the next dsk_rescnn_forward calls (which then launch kernel by kernel, not as a graph).
+ * enable = 1: CUDA events are recorded on `stream` around every kernel of the forward (order: conv1, the 11
+ * tensor-core convs in network order, pool, fc, l2norm); enable = 2: only at the section boundaries
+ * conv1 | 11 tensor-core convs | tail (3 values), so the conv chain runs back to back as in production.  dsk_get_launch_times waits for the last profiled forward (the only call in this
  * library that blocks the host) and returns its per-launch milliseconds. Used by bench.py's roofline. */
 int32_t dsk_set_profiling(dsk_handle h, int32_t enable);
 int32_t dsk_get_launch_times(dsk_handle h, float* ms_out, int32_t cap, int32_t* n_out);

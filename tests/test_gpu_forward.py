@@ -95,3 +95,65 @@ def test_rejects_bad_input(models):
         m(torch.zeros(2, 1, 64, 160, device="cuda"))       # transposed layout
     with pytest.raises(RuntimeError, match="multiple of 16"):
         m(torch.zeros(2, 1, 100, 64, device="cuda"))
+
+
+def _fresh_model(sd, env):
+    """A model whose engine handle is created under the given environment knobs (read once by dsk_create)."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        m = dsk.DeepSpeakerModel(512, 16).cuda().eval()
+        m.load_state_dict(sd)
+        with torch.no_grad():
+            m(O.make_input(1, 16, seed=1, scale=1.0).cuda())   # creates the handle now
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return m
+
+
+def test_graph_launch_equals_kernel_by_kernel(models):
+    """From the second call of a shape on, a forward is one CUDA-graph launch whose first / last kernel nodes are
+    re-pointed at the call's input / output; it must be bit-identical to the 15 plain launches (DSK_GRAPH=0)."""
+    sd, _ = models
+    mg = _fresh_model(sd, {"DSK_GRAPH": "1"})
+    mp = _fresh_model(sd, {"DSK_GRAPH": "0"})
+    with torch.no_grad():
+        for i in range(4):                      # call 0 plain (warm-up), call 1 captures, calls 2-3 re-target
+            x = O.make_input(5, 48, seed=40 + i, scale=4.0).cuda()
+            a = mg(x)
+            b = mp(x)
+            assert torch.equal(a, b), i
+        x = O.make_input(3, 32, seed=50, scale=4.0).cuda()   # a new shape drops the plan and its graph
+        assert torch.equal(mg(x), mp(x))
+        x = O.make_input(5, 48, seed=51, scale=4.0).cuda()
+        assert torch.equal(mg(x), mp(x))
+
+
+def test_graph_follows_weight_reload(models):
+    sd, _ = models
+    m = _fresh_model(sd, {"DSK_GRAPH": "1"})
+    x = O.make_input(4, 32, seed=60, scale=3.0).cuda()
+    with torch.no_grad():
+        for _ in range(3):
+            e0 = m(x)
+        m.model.fc.bias.add_(0.25)              # bumps the parameter version -> weights reloaded, plans rebuilt
+        e1 = m(x)
+        e2 = m(x)
+        ref = O.forward({k: v.cpu() for k, v in m.state_dict().items()}, x.cpu())
+    assert not torch.equal(e0, e1)
+    assert torch.equal(e1, e2)
+    assert ((e1.cpu() - ref).norm(dim=1) / ref.norm(dim=1)).max().item() < 1e-3
+
+
+def test_wide_tile_variant_is_bit_identical(models):
+    """DSK_N256=1 runs the >=256-channel convs with 128x256 tiles and single-tap weight boxes: same K order per
+    output element, so the embeddings must not change by a bit."""
+    sd, ms = models
+    mw = _fresh_model(sd, {"DSK_N256": "1", "DSK_N256_MIN_TILES": "1"})
+    x = O.make_input(9, 64, seed=70, scale=5.0).cuda()
+    with torch.no_grad():
+        assert torch.equal(mw(x), ms["fp16"](x))

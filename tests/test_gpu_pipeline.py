@@ -1,0 +1,77 @@
+"""EmbeddingPipeline (host-to-host serving path: H2D / compute lanes / D2H streams, CUDA-graph forwards, lanes that
+borrow lane 0's packed weights through dsk_share_weights) must return exactly what DeepSpeakerModel.forward returns."""
+import pytest
+import torch
+
+import deepspeaker_pytorch_b200 as dsk
+from oracle import rescnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model(cuda_dev):
+    m = dsk.DeepSpeakerModel(512, 16).to(cuda_dev).eval()
+    m.load_state_dict(O.make_state_dict(0, 16))
+    return m
+
+
+@pytest.mark.parametrize("lanes", [1, 3])
+def test_pipeline_matches_direct_forward(model, lanes):
+    pipe = dsk.EmbeddingPipeline(model, lanes=lanes)
+    n = 4 * lanes + 3                                  # every lane runs plain, capturing and re-targeted graph launches
+    xs = [O.make_input(6, 48, seed=200 + i, scale=4.0) for i in range(n)]
+    xh = [x.pin_memory() for x in xs]
+    oh = [torch.empty(6, 512).pin_memory() for _ in range(n)]
+    for i in range(n):
+        pipe.embed(xh[i], oh[i])
+    pipe.synchronize()
+    with torch.no_grad():
+        for i in range(n):
+            assert torch.equal(oh[i], model(xs[i].cuda()).cpu()), i
+    # device-resident entry point
+    with torch.no_grad():
+        outs = [pipe.embed_device(x.cuda()) for x in xs[:lanes + 1]]
+        pipe.synchronize()
+        torch.cuda.synchronize()
+        for i, e in enumerate(outs):
+            assert torch.equal(e, model(xs[i].cuda())), i
+
+
+def test_borrowing_lanes_follow_weight_updates(model):
+    pipe = dsk.EmbeddingPipeline(model, lanes=3)
+    x = O.make_input(4, 32, seed=300, scale=3.0)
+    xh, outs = x.pin_memory(), [torch.empty(4, 512).pin_memory() for _ in range(6)]
+    for k in range(3):
+        pipe.embed(xh, outs[k])
+    pipe.synchronize()
+    with torch.no_grad():
+        model.model.conv3.weight.mul_(1.25)            # parameter version bump -> lane 0 repacks, lanes 1-2 re-adopt
+    try:
+        for k in range(3, 6):
+            pipe.embed(xh, outs[k])
+        pipe.synchronize()
+        with torch.no_grad():
+            ref = model(x.cuda()).cpu()
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+        assert not torch.equal(outs[0], outs[3])
+        for k in range(3, 6):
+            assert torch.equal(outs[k], ref), k
+    finally:
+        with torch.no_grad():
+            model.model.conv3.weight.div_(1.25)
+
+
+def test_borrower_rejects_own_weights_and_training(model):
+    import ctypes
+
+    from deepspeaker_pytorch_b200 import _lib as L
+    from deepspeaker_pytorch_b200 import engine as E
+
+    e0 = model._get_engine(next(model.parameters()).device)
+    e1 = E.Engine(model, e0.device, model.operand_dtype, share_from=e0)
+    with pytest.raises(RuntimeError):
+        e1.sync_weights(eval_mode=False)
+    e0.sync_weights(True)
+    rc = e1.lib.dsk_load_weights(e1.handle, ctypes.byref(e0._wstruct), L.cur_stream())
+    assert rc != 0 and b"borrows" in e1.lib.dsk_last_error()
