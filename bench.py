@@ -493,8 +493,8 @@ def main():
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of the same 11 launches at batch 64, from the committed
-        # `ncu --set full` capture profiles/r01_final_conv_ncu_full.md (ncu flushes caches between kernels)
-        "traffic": 189381632 if (B == 64 and T == 160) else None,
+        # `ncu --set full` capture profiles/r01_final2_conv_ncu_full.md (ncu flushes caches between kernels)
+        "traffic": 194709248 if (B == 64 and T == 160) else None,
         "kernel": "conv3x3_halo_kernel: the 11 tensor-core conv launches of a step (8 x 3x3 s1 + 3 x parity-planar 5x5 s2), "
                   "timed back to back between two CUDA events on the forward's stream",
         "flop_per_launch_set": B * CONV_TC_FLOP_PER_EMB, "launch_set_ms": conv_ms,
