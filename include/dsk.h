@@ -87,7 +87,12 @@ int32_t dsk_share_weights(dsk_handle h, dsk_handle src);
 
 /* DeepSpeakerModel.forward (/root/reference/model.py:185-218), BN in eval mode
  * (train_triplet.py:332,347): x (B,1,T,64) fp32 contiguous -> emb (B,E) fp32 with ||emb||=10.
- * T must be a multiple of 16. */
+ * T must be a multiple of 16.
+ * Asynchronous on `stream`, with two exceptions that synchronise the DEVICE once: the first call of a (B, T) shape and the
+ * first call after dsk_load_weights (the plan is built and the folded BN affine is copied into the conv kernels'
+ * parameter block).  From the second call of a shape on, the 15 kernels are replayed as one CUDA graph whose first / last
+ * nodes are re-pointed at x / emb; inside a caller's own stream capture the plain launches are recorded instead (warm the
+ * shape up before capturing). */
 int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, int32_t mode,
                            void* stream);
 
