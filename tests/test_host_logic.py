@@ -59,3 +59,37 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
                 assert not re.search(r"#include.*oracle|libdsk_oracle|c_oracle", src), f
+
+
+def test_conv1_split_operand_arithmetic():
+    """csrc/conv1_umma.cuh runs conv1 (model.py:93, Cin = 1) on the tensor cores with 16-bit operand halves:
+    x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation.  Emulated here in numpy: the dropped x_lo*w_lo
+    term and the rounding of the low halves must leave the result at fp32-level accuracy (fp16 halves) and far below
+    the 16-bit rounding of the stored activation (bf16 halves)."""
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((4096, 25)) * 3.0).astype(np.float32)          # im2col rows of a normalised fbank patch
+    w = (rng.standard_normal((25, 64)) * (2.0 / (25 * 64)) ** 0.5).astype(np.float32)   # model.py:114-117 init scale
+    ref = x.astype(np.float64) @ w.astype(np.float64)
+
+    def split(a, to16):
+        hi = to16(a)
+        return hi, to16(a - hi)
+
+    def f16(a):
+        return a.astype(np.float16).astype(np.float32)
+
+    def bf16(a):                                                             # round-to-nearest-even on the top 16 bits
+        u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
+        u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+        return u.astype(np.uint32).view(np.float32)
+
+    scale = np.abs(ref).max()
+    for to16, bound in ((f16, 2e-6), (bf16, 1e-4)):
+        xh, xl = split(x, to16)
+        wh, wl = split(w, to16)
+        got = (xh + xl).astype(np.float64) @ wh.astype(np.float64) + xh.astype(np.float64) @ wl.astype(np.float64)
+        assert np.abs(got - ref).max() / scale < bound
+        plain = xh.astype(np.float64) @ wh.astype(np.float64)                # what a single 16-bit product would give
+        assert np.abs(plain - ref).max() / scale > 20 * bound
