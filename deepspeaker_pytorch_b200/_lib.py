@@ -33,28 +33,60 @@ def _sources():
     ]
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _source_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha1()
+    for s in _sources():
+        h.update(os.path.basename(s).encode())
+        with open(s, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
+    """True when lib/libdsk.so is missing or was built from different source CONTENT (file times are not trusted:
+    the tree is copied between machines, and N ranks may import it at once)."""
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(s) > t for s in _sources())
+    try:
+        with open(HASH_PATH) as f:
+            return f.read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into lib/libdsk.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into lib/libdsk.so (nvcc cross-compiles without a GPU).  Safe under concurrent
+    callers: an exclusive file lock serialises them and the library is renamed into place."""
     if not force and not needs_build():
         return LIB_PATH
+    import fcntl
+
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libdsk.so")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", LIB_PATH, os.path.join(CSRC, "dsk_api.cu")]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():  # another process built it while this one waited
+            return LIB_PATH
+        tmp = LIB_PATH + f".tmp{os.getpid()}"
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, os.path.join(CSRC, "dsk_api.cu")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, LIB_PATH)
+        with open(HASH_PATH, "w") as f:
+            f.write(_source_hash())
+        if verbose:
+            print(r.stderr)
     return LIB_PATH
 
 
@@ -129,7 +161,7 @@ _lib = None
 
 
 def load() -> ctypes.CDLL:
-    """Load libdsk.so (building it first if sources are newer). Raises if unavailable — no fallback."""
+    """Load libdsk.so (building it first if it is missing or its sources changed). Raises if unavailable — no fallback."""
     global _lib
     if _lib is not None:
         return _lib
