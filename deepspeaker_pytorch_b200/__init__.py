@@ -5,5 +5,7 @@ from .model import (DeepSpeakerModel, PairwiseDistance, TripletMarginLoss, allpa
                     select_hard_triplets)
 
 from .pipeline import EmbeddingPipeline  # noqa: F401,E402
+from .head import CrossEntropyLoss  # noqa: F401,E402
+from .optim import FusedAdagrad  # noqa: F401,E402
 
-__all__ = ["EmbeddingPipeline", "DeepSpeakerModel", "PairwiseDistance", "TripletMarginLoss", "select_hard_triplets", "allpairs_topk"]
+__all__ = ["CrossEntropyLoss", "FusedAdagrad", "EmbeddingPipeline", "DeepSpeakerModel", "PairwiseDistance", "TripletMarginLoss", "select_hard_triplets", "allpairs_topk"]

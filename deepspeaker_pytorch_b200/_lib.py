@@ -9,7 +9,7 @@ import ctypes
 import os
 import shutil
 import subprocess
-from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
@@ -155,6 +155,13 @@ SIGNATURES = {
     "dsk_gather_rows": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
     "dsk_allpairs_topk_tc": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dsk_allpairs_topk": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "dsk_linear_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "dsk_linear_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    "dsk_cross_entropy": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dsk_cross_entropy_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "dsk_adagrad_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
+                                   c_int64, c_float, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -171,6 +178,12 @@ def load() -> ctypes.CDLL:
         except Exception as e:  # a GPU box without nvcc must ship the prebuilt .so
             if not os.path.exists(LIB_PATH):
                 raise RuntimeError(f"libdsk.so is missing and could not be built: {e}") from e
+            if os.environ.get("DSK_STRICT_BUILD") == "1":
+                raise RuntimeError(f"libdsk.so does not match csrc/ and the rebuild failed: {e}") from e
+            import warnings
+
+            warnings.warn(f"libdsk.so was built from DIFFERENT sources than csrc/ and the rebuild failed ({e}); "
+                          f"loading the stale library (set DSK_STRICT_BUILD=1 to make this an error)", RuntimeWarning)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

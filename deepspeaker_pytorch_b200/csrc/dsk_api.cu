@@ -16,6 +16,7 @@
 #include "conv_umma.cuh"
 #include "conv3x3_halo.cuh"
 #include "conv1_umma.cuh"
+#include "head_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "train_kernels.cuh"
@@ -115,6 +116,19 @@ int make_tmap(CUtensorMap* out, bool bf16, const void* ptr, int rank, const uint
     return fail(DSK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims/box %s)", (int)r, rank,
                 d.c_str());
   }
+  return DSK_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember (kernel, device) pairs, not kernels.
+int ensure_smem_optin(const void* kern, int bytes) {
+  static std::map<std::pair<const void*, int>, int> done;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  auto key = std::make_pair(kern, dev);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return DSK_OK;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[key] = bytes;
   return DSK_OK;
 }
 
@@ -244,7 +258,9 @@ struct dsk_handle_s {
 
 // Everything one train-mode forward saves for its backward (one per a/p/n call, train_triplet.py:215).
 struct dsk_train_ctx_s {
-  int B = 0, T = 0;
+  int B = 0, T = 0;                    // shape the launch descriptors are currently bound to (B <= cap)
+  int cap = 0;                         // utterances the buffers were sized for
+  size_t bytes = 0;
   bool in_use = false;
   bool forward_done = false;
   const float* x = nullptr;            // borrowed: the caller keeps the input alive until backward
@@ -266,6 +282,13 @@ struct dsk_train_ctx_s {
 namespace {
 
 constexpr int kStatBlocksMax = 1200;
+// K-split count of the weight-gradient GEMM of a layer (>= 2 work items per SM), before the per-batch cap
+int wgrad_ksplit_bound(int num_sms, int cout, int cin, int taps) {
+  const bool swapped = cout == 64;
+  const int n_tile = swapped ? 64 : (cin >= 128 ? 128 : 64);
+  const int items0 = swapped ? (taps + 1) / 2 : taps * (cout / 128) * (cin / n_tile);
+  return (2 * num_sms + items0 - 1) / items0;
+}
 
 // Choose the pixel box (wt, hb, nb) with wt*hb*nb == total that wastes the fewest rows.
 void choose_tile(int B, int Hout, int Wout, int total, int& wt, int& hb, int& nb) {
@@ -288,11 +311,7 @@ void choose_tile(int B, int Hout, int Wout, int total, int& wt, int& hb, int& nb
 template <int N_TILE, bool BF16, bool OUT_F32 = false>
 int launch_conv_t(const ConvLaunch& L, cudaStream_t s) {
   auto kern = dsk::conv_umma_kernel<N_TILE, BF16, OUT_F32>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dsk::ConvSmem<N_TILE>::kTotal));
-    attr_set = true;
-  }
+  if (int rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), dsk::ConvSmem<N_TILE>::kTotal)) return rc;
   CUDA_TRY(launch_pdl(kern, dim3(L.grid), dim3(dsk::kConvThreads), dsk::ConvSmem<N_TILE>::kTotal, s, L.tmA, L.tmB, L.tmOut, L.tmRes, L.p));
   return DSK_OK;
 }
@@ -529,6 +548,7 @@ int build_wgrad(const dsk_handle_s* h, WgradLaunch* L, const void* G, const void
   if (ksplit > max_split) ksplit = max_split;
   if (ksplit < 1) ksplit = 1;
   p.ksplit = ksplit;
+  p.slice_elems = static_cast<long>(p.taps) * cout * cin;
   const int items = items0 * ksplit;
   L->grid = items < h->num_sms ? items : h->num_sms;
   const View5 g = nhwc_view(G, B, Hout, Wout, cout);
@@ -542,11 +562,7 @@ int build_wgrad(const dsk_handle_s* h, WgradLaunch* L, const void* G, const void
 template <int N_TILE, bool BF16>
 int launch_wgrad_t(const WgradLaunch& L, cudaStream_t s) {
   auto kern = dsk::wgrad_umma_kernel<N_TILE, BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dsk::WgradSmem<N_TILE>::kTotal));
-    attr_set = true;
-  }
+  if (int rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), dsk::WgradSmem<N_TILE>::kTotal)) return rc;
   kern<<<L.grid, 256, dsk::WgradSmem<N_TILE>::kTotal, s>>>(L.tmG, L.tmX, L.p);
   KERNEL_CHECK();
   return DSK_OK;
@@ -764,11 +780,7 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
 template <int N_TILE, bool BF16>
 int launch_halo_t(const HaloLaunch& L, cudaStream_t s) {
   auto kern = dsk::conv3x3_halo_kernel<N_TILE, BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  if (int rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
   CUDA_TRY(launch_pdl(kern, dim3(L.grid), dim3(dsk::kHaloThreads), L.smem, s, L.tmIn, L.tmW, L.tmOut, L.tmRes, L.p));
   return DSK_OK;
 }
@@ -799,7 +811,7 @@ void act_shape(int i, int T, int& H, int& W, int& C) {
   C = 64 << st;
 }
 
-int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
+int get_plan(dsk_handle h, int B, int T, cudaStream_t s, dsk_handle_s::Plan** out) {
   auto key = std::make_pair(B, T);
   auto it = h->plans.find(key);
   if (it != h->plans.end()) {
@@ -840,7 +852,10 @@ int get_plan(dsk_handle h, int B, int T, dsk_handle_s::Plan** out) {
     // find non-zero pads after this one ran, so only one shape is cached at a time
     h->plans.clear();
   }
-  CUDA_TRY(cudaMemset(h->ws, 0, act_bytes));
+  // Ordered on the caller's stream: after the forwards this lane still has in flight on it (they read / write the old
+  // shape's pads) and before the new shape's first kernel.  (A NULL-stream memset would be unordered against the
+  // non-blocking streams PyTorch hands out.)
+  CUDA_TRY(cudaMemsetAsync(h->ws, 0, act_bytes, s));
   dsk_handle_s::Plan pl;
   pl.B = B;
   pl.T = T;
@@ -1136,11 +1151,7 @@ int enqueue_forward(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B,
                           pl->pooled, H4, WC, 512, 1));
     mark();
     const int fc_smem = (dsk::kFcUtt + dsk::kFcFeat) * dsk::kFcPitch * 4;
-    static bool fc_attr = false;
-    if (!fc_attr) {
-      CUDA_TRY(cudaFuncSetAttribute(dsk::fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem));
-      fc_attr = true;
-    }
+    if (int rc2 = ensure_smem_optin(reinterpret_cast<const void*>(dsk::fc_kernel), fc_smem)) return rc2;
     dim3 g((B + dsk::kFcUtt - 1) / dsk::kFcUtt, h->emb / dsk::kFcFeat, dsk::kFcSplit);
     CUDA_TRY(launch_pdl(dsk::fc_kernel, g, dim3(256), fc_smem, s, (const float*)pl->pooled, (const float*)h->fc_wq,
                         pl->fc_part, B, 2048, h->emb));
@@ -1258,7 +1269,7 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
   if (mode != DSK_EVAL) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: use dsk_rescnn_forward_train for batch-statistics BN");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dsk_handle_s::Plan* pl;
-  rc = get_plan(h, B, T, &pl);
+  rc = get_plan(h, B, T, s, &pl);
   if (rc) return rc;
   if (h->use_graph && !h->profiling && !h->trace && pl->warm) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1305,10 +1316,17 @@ static int stat_blocks(long M, int C) {
   return gx < 1 ? 1 : static_cast<int>(gx);
 }
 
-static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
+// Buffers of a train context are sized for `cap` utterances; the launch descriptors (TMA maps, tile counts) are bound
+// to the batch size of the current forward (ctx_bind), so one context serves every B <= cap of the same T: the
+// reference's hard-triplet branch re-forwards a different number of selected triplets every step
+// (train_triplet.py:262-279) and must not allocate a fresh context per distinct count.
+static int ctx_bind(dsk_handle h, dsk_train_ctx_s* c, int B);
+
+static int ctx_create(dsk_handle h, int cap, int T, cudaStream_t s, dsk_train_ctx_s** out) {
   dsk_train_ctx_s* c = new dsk_train_ctx_s();
-  c->B = B;
+  c->cap = cap;
   c->T = T;
+  const int B = cap;
   size_t bytes = 0;
   auto take = [&](size_t n) {
     const size_t o = bytes;
@@ -1332,10 +1350,22 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
   const size_t o_inv = take(B * 4), o_sc = take(512 * 4), o_sh = take(512 * 4);
   const size_t o_part = take(static_cast<size_t>(kStatBlocksMax) * 2 * 512 * 4), o_coef = take(3 * 512 * 4);
   const size_t o_gfc = take(static_cast<size_t>(B) * h->emb * 4), o_dP = take(static_cast<size_t>(B) * 2048 * 4);
-  const size_t o_dw = take(static_cast<size_t>(25) * 512 * 256 * 4), o_c1 = take(static_cast<size_t>(B) * ((T / 2 + 7) / 8) * 1600 * 4);
+  size_t dw_bytes = 0;  // [ksplit][tap][cout][cin] fp32 slices of the largest layer
+  for (int i = 1; i < DSK_NUM_CONV; ++i) {
+    const LayerCfg lc = layer_cfg(i);
+    const int taps = lc.ksize * lc.ksize;
+    const size_t need = static_cast<size_t>(wgrad_ksplit_bound(h->num_sms, lc.cout, lc.cin, taps)) * taps * lc.cout * lc.cin * 4;
+    if (need > dw_bytes) dw_bytes = need;
+  }
+  const size_t o_dw = take(dw_bytes), o_c1 = take(static_cast<size_t>(B) * ((T / 2 + 7) / 8) * 1600 * 4);
   const size_t o_gA = take(max_act), o_gB = take(max_act), o_G = take(max_act), o_gres = take(max_act);
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->base), bytes));
-  CUDA_TRY(cudaMemset(c->base, 0, bytes));
+  if (cudaMalloc(reinterpret_cast<void**>(&c->base), bytes) != cudaSuccess) {
+    cudaGetLastError();
+    delete c;
+    return fail(DSK_ERR_CUDA, "train context: cudaMalloc of %zu bytes failed", bytes);
+  }
+  c->bytes = bytes;
+  CUDA_TRY(cudaMemsetAsync(c->base, 0, bytes, s));
   uint8_t* b = c->base;
   for (int i = 0; i < DSK_NUM_CONV; ++i) {
     c->raw[i] = reinterpret_cast<float*>(b + o_raw[i]);
@@ -1359,7 +1389,15 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
   c->gB = b + o_gB;
   c->G = b + o_G;
   c->gres = b + o_gres;
-  // launch descriptors
+  *out = c;
+  return DSK_OK;
+}
+
+// (re)build the launch descriptors for batch size B (every tensor is a contiguous [B][H][W][C] prefix of its buffer)
+static int ctx_bind(dsk_handle h, dsk_train_ctx_s* c, int B) {
+  if (c->B == B) return DSK_OK;
+  const int T = c->T;
+  c->B = 0;
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
     const LayerCfg lc = layer_cfg(i);
     int Hi, Wi, Ci, Ho, Wo, Co;
@@ -1383,7 +1421,35 @@ static int ctx_create(dsk_handle h, int B, int T, dsk_train_ctx_s** out) {
     rc = build_wgrad(h, &c->wgrad[i], c->G, c->y[i - 1], B, Hi, Wi, lc.cout, lc.cin, lc.ksize, lc.stride, c->dwacc);
     if (rc) return rc;
   }
-  *out = c;
+  c->B = B;
+  return DSK_OK;
+}
+
+// A free context of the same T with room for B utterances (the smallest such), else a new one of capacity B after
+// returning the idle contexts it makes redundant (smaller capacity or another T) to the driver: the pool holds the
+// contexts a step has in flight at once (3 for a triplet step), not one per batch size ever seen.
+static int ctx_acquire(dsk_handle h, int B, int T, cudaStream_t s, dsk_train_ctx_s** out) {
+  dsk_train_ctx_s* best = nullptr;
+  for (dsk_train_ctx_s* cand : h->ctx_pool)
+    if (!cand->in_use && cand->T == T && cand->cap >= B && (!best || cand->cap < best->cap)) best = cand;
+  if (!best) {
+    for (size_t i = 0; i < h->ctx_pool.size();) {
+      dsk_train_ctx_s* c = h->ctx_pool[i];
+      if (!c->in_use && (c->T != T || c->cap < B)) {
+        CUDA_TRY(cudaFree(c->base));  // synchronises the device: nothing still reads the buffers
+        delete c;
+        h->ctx_pool.erase(h->ctx_pool.begin() + i);
+      } else {
+        ++i;
+      }
+    }
+    int rc = ctx_create(h, B, T, s, &best);
+    if (rc) return rc;
+    h->ctx_pool.push_back(best);
+  }
+  int rc = ctx_bind(h, best, B);
+  if (rc) return rc;
+  *out = best;
   return DSK_OK;
 }
 
@@ -1414,16 +1480,8 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
   if (T < 16 || T % 16) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward_train: T must be a positive multiple of 16 (got %d)", T);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dsk_train_ctx_s* c = nullptr;
-  for (dsk_train_ctx_s* cand : h->ctx_pool)
-    if (!cand->in_use && cand->B == B && cand->T == T) {
-      c = cand;
-      break;
-    }
-  if (!c) {
-    rc = ctx_create(h, B, T, &c);
-    if (rc) return rc;
-    h->ctx_pool.push_back(c);
-  }
+  rc = ctx_acquire(h, B, T, s, &c);
+  if (rc) return rc;
   c->in_use = true;
   c->forward_done = false;
   c->x = x;
@@ -1464,7 +1522,8 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
     else dsk::pool_time_kernel<false><<<dim3(B, WC / 512), 256, 0, s>>>((const uint16_t*)c->y[11], c->pooled, H4, WC, 512, 0);
     KERNEL_CHECK();
     const int fc_smem = (dsk::kFcUtt + dsk::kFcFeat) * dsk::kFcPitch * 4;
-    CUDA_TRY(cudaFuncSetAttribute(dsk::fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem));
+    rc = ensure_smem_optin(reinterpret_cast<const void*>(dsk::fc_kernel), fc_smem);
+    if (rc) return rc;
     dim3 g((B + dsk::kFcUtt - 1) / dsk::kFcUtt, h->emb / dsk::kFcFeat, dsk::kFcSplit);
     dsk::fc_kernel<<<g, 256, fc_smem, s>>>(c->pooled, h->fc_wq, c->fc_part, B, 2048, h->emb);
     KERNEL_CHECK();
@@ -1536,11 +1595,10 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
     } else {
       const int taps = lc.ksize * lc.ksize;
       const size_t n = static_cast<size_t>(taps) * lc.cout * lc.cin;
-      CUDA_TRY(cudaMemsetAsync(c->dwacc, 0, n * 4, s));
       rc = launch_wgrad(h, c->wgrad[i], s);
       if (rc) return rc;
       dsk::unpack_wgrad_kernel<<<static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, s>>>(
-          c->dwacc, g->conv_w[i], lc.cout, lc.cin, taps, invS);
+          c->dwacc, g->conv_w[i], lc.cout, lc.cin, taps, invS, c->wgrad[i].p.ksplit, c->wgrad[i].p.slice_elems);
       KERNEL_CHECK();
       for (int k = 0; k < c->n_dgrad[i]; ++k) {
         rc = launch_conv(h, c->dgrad[i][k], s);
@@ -1629,14 +1687,15 @@ int32_t dsk_conv2d_wgrad_nhwc(dsk_handle h, const void* G, const void* X, float*
   const int taps = ksize * ksize;
   const size_t n = static_cast<size_t>(taps) * cout * cin;
   float* acc = nullptr;
-  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&acc), n * 4, s));
-  CUDA_TRY(cudaMemsetAsync(acc, 0, n * 4, s));
   WgradLaunch L;
-  rc = build_wgrad(h, &L, G, X, B, Hin, Win, cout, cin, ksize, stride, acc);
-  if (!rc) rc = launch_wgrad(h, L, s);
+  rc = build_wgrad(h, &L, G, X, B, Hin, Win, cout, cin, ksize, stride, nullptr);
+  if (rc) return rc;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&acc), n * 4 * L.p.ksplit, s));
+  L.p.dw = acc;
+  rc = launch_wgrad(h, L, s);
   if (!rc) {
     dsk::unpack_wgrad_kernel<<<static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, s>>>(
-        acc, dw_oihw, cout, cin, taps, mult);
+        acc, dw_oihw, cout, cin, taps, mult, L.p.ksplit, L.p.slice_elems);
     KERNEL_CHECK();
   }
   CUDA_TRY(cudaFreeAsync(acc, s));
@@ -1945,6 +2004,78 @@ int32_t dsk_allpairs_topk(const float* E, const int64_t* labels, int32_t N, int3
   dsk::topk_rows_kernel<<<(N + 7) / 8, 256, 0, s>>>(S, labels, N, pd_eps(D), k, idx, val);
   KERNEL_CHECK();
   CUDA_TRY(cudaFreeAsync(S, s));
+  return DSK_OK;
+}
+
+// ---- classifier head, cross-entropy, fused optimizer step ---------------------------------------------------------
+int32_t dsk_linear_forward(const float* x, const float* w, const float* b, int32_t M, int32_t N, int32_t K, float* y,
+                           void* stream) {
+  if (!x || !w || !y || M <= 0 || N <= 0 || K <= 0) return fail(DSK_ERR_INVALID, "dsk_linear_forward: bad arguments");
+  dim3 g((N + dsk::kGemmTile - 1) / dsk::kGemmTile, (M + dsk::kGemmTile - 1) / dsk::kGemmTile);
+  // y[i][j] = sum_k x[i][k] * w[j][k] + b[j]
+  dsk::sgemm_strided_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, K, 1, w, 1, K, b, y, M, N, K);
+  KERNEL_CHECK();
+  return DSK_OK;
+}
+
+int32_t dsk_linear_backward(const float* x, const float* w, const float* gy, int32_t M, int32_t N, int32_t K, float* gx,
+                            float* gw, float* gb, void* stream) {
+  if (!x || !w || !gy || M <= 0 || N <= 0 || K <= 0) return fail(DSK_ERR_INVALID, "dsk_linear_backward: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int T = dsk::kGemmTile;
+  if (gx) {  // gx[i][k] = sum_j gy[i][j] * w[j][k]
+    dsk::sgemm_strided_kernel<<<dim3((K + T - 1) / T, (M + T - 1) / T), 256, 0, s>>>(gy, N, 1, w, K, 1, nullptr, gx, M, K, N);
+    KERNEL_CHECK();
+  }
+  if (gw) {  // gw[j][k] = sum_i gy[i][j] * x[i][k]
+    dsk::sgemm_strided_kernel<<<dim3((K + T - 1) / T, (N + T - 1) / T), 256, 0, s>>>(gy, 1, N, x, K, 1, nullptr, gw, N, K, M);
+    KERNEL_CHECK();
+  }
+  if (gb) {
+    dsk::colsum_kernel<<<(N + 127) / 128, 128, 0, s>>>(gy, M, N, gb);
+    KERNEL_CHECK();
+  }
+  return DSK_OK;
+}
+
+int32_t dsk_cross_entropy(const float* logits, const int64_t* labels, int32_t M, int32_t C, float* loss, float* lse,
+                          float* row_loss, void* stream) {
+  if (!logits || !labels || !loss || !lse || !row_loss || M <= 0 || C <= 0)
+    return fail(DSK_ERR_INVALID, "dsk_cross_entropy: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dsk::ce_rows_kernel<<<M, 256, 0, s>>>(logits, labels, C, lse, row_loss);
+  KERNEL_CHECK();
+  dsk::mean_rows_kernel<<<1, 1024, 0, s>>>(row_loss, M, loss);
+  KERNEL_CHECK();
+  return DSK_OK;
+}
+
+int32_t dsk_cross_entropy_bwd(const float* logits, const int64_t* labels, const float* lse, const float* grad_loss,
+                              int32_t M, int32_t C, float* dlogits, void* stream) {
+  if (!logits || !labels || !lse || !grad_loss || !dlogits || M <= 0 || C <= 0)
+    return fail(DSK_ERR_INVALID, "dsk_cross_entropy_bwd: bad arguments");
+  const long total = static_cast<long>(M) * C;
+  const int blocks = static_cast<int>((total + 255) / 256 < 2368 ? (total + 255) / 256 : 2368);
+  dsk::ce_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, labels, lse, grad_loss, M, C, dlogits);
+  KERNEL_CHECK();
+  return DSK_OK;
+}
+
+int32_t dsk_adagrad_step(float* param, const float* grad, float* state_sum, int64_t n, double lr, double lr_decay,
+                         double weight_decay, double eps, int64_t step, float grad_mult, const float* grad_denom,
+                         void* stream) {
+  if (!param || !grad || !state_sum || n <= 0 || step < 1)
+    return fail(DSK_ERR_INVALID, "dsk_adagrad_step: bad arguments (step counts from 1)");
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(state_sum)) & 15)
+    return fail(DSK_ERR_INVALID, "dsk_adagrad_step: buffers must be 16-byte aligned");
+  // clr as torch computes it (Python double arithmetic, then one rounding to float at the kernel boundary)
+  const double minus_clr = -lr / (1.0 + static_cast<double>(step - 1) * lr_decay);
+  const long n4 = n / 4 > 0 ? n / 4 : 1;
+  const int blocks = static_cast<int>((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  dsk::adagrad_flat_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, state_sum, n, grad_mult, grad_denom, static_cast<float>(minus_clr), static_cast<float>(eps),
+      static_cast<float>(weight_decay));
+  KERNEL_CHECK();
   return DSK_OK;
 }
 

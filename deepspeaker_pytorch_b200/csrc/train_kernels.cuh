@@ -487,17 +487,20 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int nblk,
   out[i] = static_cast<float>(tot) * mult;
 }
 
-// dW fp32 [tap][co][ci] (accumulated by the wgrad GEMM) -> OIHW [co][ci][tap] scaled by mult.
+// K-split partial weight gradients fp32 [ksplit][tap][co][ci] (one slice per split of the wgrad GEMM) -> OIHW
+// [co][ci][tap], slices added in fixed order (deterministic), scaled by mult.  Reads are coalesced along ci.
 __global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restrict__ out, int cout, int cin, int taps,
-                                    float mult) {
+                                    float mult, int ksplit, long slice_elems) {
   const long total = static_cast<long>(cout) * cin * taps;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int tap = i % taps;
-    const long r = i / taps;
-    const int ci = r % cin;
-    const int co = r / cin;
-    out[i] = in[(static_cast<long>(tap) * cout + co) * cin + ci] * mult;
+    const int ci = i % cin;
+    const long r = i / cin;
+    const int co = r % cout;
+    const int tap = r / cout;
+    float acc = in[i];
+    for (int k = 1; k < ksplit; ++k) acc += in[k * slice_elems + i];
+    out[(static_cast<long>(co) * cin + ci) * taps + tap] = acc * mult;
   }
 }
 

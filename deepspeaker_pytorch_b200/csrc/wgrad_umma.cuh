@@ -11,9 +11,11 @@
 // stride, stride byte offset = 1024 B between 8-pixel groups, major bits = MN).  The tap shift and the zero padding
 // are TMA coordinates on the outer (w, h) dims exactly as in the forward conv, so no transposed copies exist.
 //
-// Work item = (tap, 128 output channels, N_TILE input channels, K split); partial tiles are reduced with fp32
-// atomics into dW.  Layers with 64 output channels use the swapped form (M = two taps x 64 input channels,
-// N = 64 output channels) so that the MMA still has M = 128.
+// Work item = (tap, 128 output channels, N_TILE input channels, K split).  Every K split writes its partial tile with
+// plain stores into its OWN slice dw[ks][tap][cout][cin]; unpack_wgrad_kernel then adds the slices in fixed order, so
+// the weight gradient is bit-reproducible from run to run (no atomics, no pre-zeroing).  Layers with 64 output
+// channels use the swapped form (M = two taps x 64 input channels, N = 64 output channels) so that the MMA still
+// has M = 128.
 #pragma once
 #include "conv_umma.cuh"
 
@@ -31,7 +33,8 @@ struct WgradParams {
   int8_t tap_dw[kMaxTaps];
   int8_t tap_ph[kMaxTaps];
   int8_t tap_dh[kMaxTaps];
-  float* dw;                // fp32 [tap][cout][cin], pre-zeroed
+  float* dw;                // fp32 [ksplit][tap][cout][cin]: one slice per K split, every element written exactly once
+  long slice_elems;         // taps * cout * cin
 };
 
 template <int N_TILE>
@@ -102,7 +105,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   // item -> (tap unit, co tile, ci tile, K range); K split fastest
-  auto decode = [&](int item, int& tu, int& co0, int& ci0, int& k_begin, int& k_end) {
+  auto decode = [&](int item, int& tu, int& co0, int& ci0, int& k_begin, int& k_end) -> int {
     const int ks = item % p.ksplit;
     int r = item / p.ksplit;
     const int cit = r % p.ci_tiles;
@@ -114,6 +117,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const int per = (total_chunks + p.ksplit - 1) / p.ksplit;
     k_begin = ks * per;
     k_end = k_begin + per < total_chunks ? k_begin + per : total_chunks;
+    return ks;
   };
 
   if (warp == 0) {
@@ -203,32 +207,40 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int tu, co0, ci0, kb, ke;
-      decode(item, tu, co0, ci0, kb, ke);
+      const int ks = decode(item, tu, co0, ci0, kb, ke);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      // destination of D[row][col]
-      float* dst;
-      long col_stride;
-      bool live = ke > kb;
+      // destination of D[row][col] inside this K split's slice; an empty K range (split rounding) stores zeros
+      float* dst = p.dw + static_cast<long>(ks) * p.slice_elems;
+      const bool empty = ke <= kb;
+      bool live = true;
       if (!p.swapped) {
         const int co = co0 + row;
-        live = live && co < p.cout;
-        dst = p.dw + (static_cast<long>(tu) * p.cout + co) * p.cin + ci0;
-        col_stride = 1;
+        live = co < p.cout;
+        dst += (static_cast<long>(tu) * p.cout + co) * p.cin + ci0;
       } else {
         const int tap = 2 * tu + (row >> 6);
-        live = live && tap < p.taps;
-        dst = p.dw + static_cast<long>(tap) * p.cout * p.cin + (row & 63);  // [tap][co = col][ci = row % 64]
-        col_stride = p.cin;
+        live = tap < p.taps;
+        dst += static_cast<long>(tap) * p.cout * p.cin + (row & 63);  // [tap][co = col][ci = row % 64]
       }
 #pragma unroll 1
       for (int j = 0; j < N_TILE / 32; ++j) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 32, v);
         tmem_ld_wait();
-        if (live) {
+        if (empty) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) atomicAdd(dst + (j * 32 + e) * col_stride, __uint_as_float(v[e]));
+          for (int e = 0; e < 32; ++e) v[e] = 0u;
+        }
+        if (live) {
+          if (!p.swapped) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              *reinterpret_cast<uint4*>(dst + j * 32 + e * 4) = make_uint4(v[e * 4], v[e * 4 + 1], v[e * 4 + 2], v[e * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) dst[static_cast<long>(j * 32 + e) * p.cin] = __uint_as_float(v[e]);
+          }
         }
       }
       tc_fence_before();

@@ -75,8 +75,16 @@ class Engine:
                self.train_calls if eval_mode else 0]
         return tuple(vs)
 
+    def invalidate(self):
+        """Force a repack / BN re-fold at the next forward.  Change detection relies on ``tensor._version`` (bumped by
+        every in-place op on the parameter itself, which is what optimizers and ``load_state_dict`` do) and on
+        ``data_ptr``; writes through ``param.data`` / ``buffer.data`` (``p.data.fill_()``, ``p.data.copy_()``, the
+        reference's init idiom, model.py:114-120) do NOT bump the version: call this (or
+        ``DeepSpeakerModel.refresh_weights()``) after such a write."""
+        self._versions = None
+
     def sync_weights(self, eval_mode=True):
-        """Repack/fold when any parameter (or, in eval, BN buffer) changed since the last call."""
+        """Repack/fold when any parameter (or, in eval, BN buffer) changed since the last call (see ``invalidate``)."""
         if self.share_from is not None:
             if not eval_mode:
                 raise RuntimeError("an engine that borrows its weights is inference-only")

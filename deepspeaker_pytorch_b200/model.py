@@ -21,6 +21,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import engine as _engine
+from . import head as _head
 
 
 class ReLU(nn.Hardtanh):
@@ -105,6 +106,14 @@ class DeepSpeakerModel(nn.Module):
             self._engine = _engine.Engine(self, device, self.operand_dtype)
         return self._engine
 
+    def refresh_weights(self):
+        """Tell the engine(s) that parameters / BatchNorm buffers were modified through ``.data`` (which PyTorch's
+        version counter does not see): the packed 16-bit weights and the folded BN affine are rebuilt at the next
+        forward.  In-place updates of the parameters themselves (optimizers, ``load_state_dict``) are detected
+        automatically."""
+        if self._engine is not None:
+            self._engine.invalidate()
+
     def l2_norm(self, input):
         """model.py:172-183 (kept for API parity; the engine fuses it into the tail kernel)."""
         input_size = input.size()
@@ -125,9 +134,11 @@ class DeepSpeakerModel(nn.Module):
         return self.features
 
     def forward_classifier(self, x):
-        """model.py:220-223."""
+        """model.py:220-223: embeddings -> ``model.classifier`` logits (B, num_classes), on the repo's fp32 GEMM
+        kernels (``dsk_linear_forward/backward``); ``model.classifier`` only holds the parameters."""
         features = self.forward(x)
-        return self.model.classifier(features)
+        c = self.model.classifier
+        return _head.LinearFn.apply(features, c.weight, c.bias)
 
 
 class PairwiseDistance:

@@ -50,14 +50,25 @@ class EmbeddingPipeline:
     @torch.no_grad()
     def embed_device(self, x: torch.Tensor) -> torch.Tensor:
         """Queue one device-resident batch on the next compute lane; returns the (asynchronously produced) embeddings.
-        The caller orders its own streams against ``lane_of(result)`` / ``synchronize()``."""
+
+        Lifetimes: ``x`` may be dropped by the caller right after this call (it is recorded on the lane stream, so the
+        caching allocator does not recycle its block before the forward has read it).  The returned ``emb`` is
+        produced on the lane stream: order the consuming stream with ``wait_lanes()`` / ``synchronize()`` before
+        reading it, and call ``emb.record_stream(consumer)`` if it is consumed on another stream and then dropped."""
         lane = self._i % len(self.lanes)
         self._i += 1
         st = self.lanes[lane]
         st.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(st):
             emb = self.engines[lane].forward(x, False)
+        x.record_stream(st)
         return emb
+
+    def wait_lanes(self, stream=None):
+        """Make ``stream`` (default: the current stream) wait for everything queued on the compute lanes."""
+        stream = stream or torch.cuda.current_stream(self.device)
+        for st in self.lanes:
+            stream.wait_stream(st)
 
     @torch.no_grad()
     def embed(self, x_host: torch.Tensor, out_host: torch.Tensor) -> torch.cuda.Event:

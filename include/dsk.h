@@ -88,9 +88,12 @@ int32_t dsk_share_weights(dsk_handle h, dsk_handle src);
 /* DeepSpeakerModel.forward (/root/reference/model.py:185-218), BN in eval mode
  * (train_triplet.py:332,347): x (B,1,T,64) fp32 contiguous -> emb (B,E) fp32 with ||emb||=10.
  * T must be a multiple of 16.
- * Asynchronous on `stream`, with two exceptions that synchronise the DEVICE once: the first call of a (B, T) shape and the
- * first call after dsk_load_weights (the plan is built and the folded BN affine is copied into the conv kernels'
- * parameter block).  From the second call of a shape on, the 15 kernels are replayed as one CUDA graph whose first / last
+ * Asynchronous on `stream`, with one exception that synchronises the DEVICE: the first forward after
+ * dsk_load_weights (the folded BN affine is copied to the host and baked into the conv kernels' parameter block).
+ * The first call of a new (B, T) shape rebuilds the plan and re-zeroes the padded activation workspace with a
+ * memset ORDERED ON `stream` (after the forwards this handle still has in flight there); if the workspace has to
+ * grow, cudaFree synchronises the device.  One handle must only be driven from one stream at a time (use one handle
+ * per compute lane, dsk_share_weights).  From the second call of a shape on, the 15 kernels are replayed as one CUDA graph whose first / last
  * nodes are re-pointed at x / emb; inside a caller's own stream capture the plain launches are recorded instead (warm the
  * shape up before capturing). */
 int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, int32_t mode,
@@ -207,6 +210,32 @@ int32_t dsk_allpairs_topk_tc(dsk_handle h, const float* E, const int64_t* labels
                              int64_t* idx, float* val, void* stream);
 int32_t dsk_allpairs_topk(const float* E, const int64_t* labels, int32_t N, int32_t D, int32_t k, int64_t* idx,
                           float* val, void* stream);
+
+/* nn.Linear of DeepSpeakerModel.forward_classifier (/root/reference/model.py:167,220-223): y (M,N) = x (M,K) w(N,K)^T + b.
+ * fp32 on the CUDA cores, fixed summation order (deterministic).  b may be NULL. */
+int32_t dsk_linear_forward(const float* x, const float* w, const float* b, int32_t M, int32_t N, int32_t K, float* y,
+                           void* stream);
+/* its backward: gx (M,K) = gy w, gw (N,K) = gy^T x, gb (N) = column sums of gy; any output pointer may be NULL. */
+int32_t dsk_linear_backward(const float* x, const float* w, const float* gy, int32_t M, int32_t N, int32_t K, float* gx,
+                            float* gw, float* gb, void* stream);
+/* nn.CrossEntropyLoss() over (M,C) logits and int64 labels (/root/reference/train_triplet.py:281-285):
+ * loss (1,) = mean_i (logsumexp_j logits[i] - logits[i][label_i]); also writes lse (M,) and row_loss (M,) (workspace
+ * the backward reads).  A label outside [0,C) yields NaN. */
+int32_t dsk_cross_entropy(const float* logits, const int64_t* labels, int32_t M, int32_t C, float* loss, float* lse,
+                          float* row_loss, void* stream);
+/* dlogits (M,C) = (softmax(logits) - onehot(labels)) * grad_loss / M; grad_loss is a device scalar. */
+int32_t dsk_cross_entropy_bwd(const float* logits, const int64_t* labels, const float* lse, const float* grad_loss,
+                              int32_t M, int32_t C, float* dlogits, void* stream);
+
+/* torch.optim.Adagrad step (/root/reference/train_triplet.py:369-383, called at :224,291) on ONE flat bucket of n fp32
+ * elements (parameters, gradients and the running sum of squares laid out identically), fused with the gradient scale
+ * that follows the data-parallel allreduce:  g = grad * grad_mult (/ *grad_denom if non-NULL, a device scalar);
+ * g += weight_decay * p;  sum = fma(g, g, sum);  p += (g * -clr) / (sqrt(sum) + eps),  clr = lr / (1 + (step-1) lr_decay).
+ * `step` counts from 1.  Operation order = torch's foreach Adagrad, so the result is bit-identical to it.
+ * Buffers must be 16-byte aligned. */
+int32_t dsk_adagrad_step(float* param, const float* grad, float* state_sum, int64_t n, double lr, double lr_decay,
+                         double weight_decay, double eps, int64_t step, float grad_mult, const float* grad_denom,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,35 +112,56 @@ def l2_norm(x):
     return torch.div(x, norm.view(-1, 1).expand_as(x))
 
 
+class _ClipForcedMask(torch.autograd.Function):
+    """clamp(x, 0, 20) whose backward passes the gradient where `mask` says so instead of where 0 < x < 20.
+    Test-only: lets a test differentiate the oracle with the SAME pass-through set as the implementation under test.
+    The clip gradient is discontinuous, so an element whose pre-activation lies within rounding distance of 0 or 20
+    flips between implementations, and ONE flipped element moves every upstream gradient by ~1/sqrt(#elements)
+    (2.5e-3 at batch 6: fp32 vs fp64 of this very oracle differ by that much, tests/test_oracle_golden.py)."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        ctx.save_for_backward(mask)
+        return torch.clamp(x, 0.0, CLIP_HI)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return g * mask.to(g.dtype), None
+
+
 def _ste(t, dtype):
     """Round to `dtype` in the forward, identity in the backward (straight-through)."""
-    return t if dtype is None else t + (t.to(dtype).float() - t).detach()
+    return t if dtype is None else t + (t.to(dtype).to(t.dtype) - t).detach()
 
 
-def forward(sd, x, train: bool = False, stats_out=None, taps=None, storage=None):
+def forward(sd, x, train: bool = False, stats_out=None, taps=None, storage=None, masks=None):
     """DeepSpeakerModel.forward, model.py:185-218. x (B,1,T,64) fp32 -> (B,E), ||.|| = 10.
     taps: optional dict collecting per-layer activations (NCHW) keyed by conv index 0..11.
     storage: None = the reference's fp32 arithmetic.  torch.float16 / torch.bfloat16 = additionally round what
     the CUDA engine stores in 16 bit (tensor-core conv weights and every post-activation tensor; conv1, the
     pre-BN conv outputs and the tail stay fp32).  Only used by tests that need the same ReLU/clip masks as the
-    engine to validate its backward kernels in isolation."""
+    engine to validate its backward kernels in isolation.
+    masks: optional {conv index 0..11: bool NCHW tensor}: the clip of that layer back-propagates through exactly these
+    elements (see _ClipForcedMask); forward values are unaffected.  Works in fp64 when sd and x are fp64."""
     q = lambda t: _ste(t, storage)
+    clip = lambda t, i: clipped_relu(t) if masks is None else _ClipForcedMask.apply(t, masks[i])
     h = x
     for s in range(4):
         pre = f"model.layer{s + 1}.0"
         w_in = sd[f"model.conv{s + 1}.weight"]
         h = F.conv2d(h, w_in if s == 0 else q(w_in), None, 2, 2)              # model.py:187,192,197,202
-        h = q(clipped_relu(_bn(h, sd, f"model.bn{s + 1}", train, stats_out)))  # :188-189
+        h = q(clip(_bn(h, sd, f"model.bn{s + 1}", train, stats_out), 3 * s))  # :188-189
         if taps is not None:
             taps[3 * s] = h
         res = h                                                                # BasicBlock.forward :66-82
         t = F.conv2d(h, q(sd[pre + ".conv1.weight"]), None, 1, 1)
-        t = q(clipped_relu(_bn(t, sd, pre + ".bn1", train, stats_out)))
+        t = q(clip(_bn(t, sd, pre + ".bn1", train, stats_out), 3 * s + 1))
         if taps is not None:
             taps[3 * s + 1] = t
         t = F.conv2d(t, q(sd[pre + ".conv2.weight"]), None, 1, 1)
         t = _bn(t, sd, pre + ".bn2", train, stats_out)
-        h = q(clipped_relu(t + res))                                           # :79-80
+        h = q(clip(t + res, 3 * s + 2))                                        # :79-80
         if taps is not None:
             taps[3 * s + 2] = h
     h = h.mean(dim=2, keepdim=True)                                            # AdaptiveAvgPool2d((1,None)) :111,207
@@ -199,18 +220,20 @@ def allpairs_topk(E, labels, k: int):
     return idx, val
 
 
-def triplet_step_branch_a(sd, xa, xp, xn, margin: float, stats_out=None, storage=None):
+def triplet_step_branch_a(sd, xa, xp, xn, margin: float, stats_out=None, storage=None, masks=None, taps=None):
     """Branch A of the training step (epoch > min_softmax_epoch), train_triplet.py:215-224:
     three separate train-mode forwards (BN statistics per call, running stats updated three times),
-    triplet loss over all triplets, backward.  Returns (loss, grads dict, out_a, out_p, out_n)."""
+    triplet loss over all triplets, backward.  Returns (loss, grads dict, out_a, out_p, out_n).
+    masks / taps: optional lists of three per-call dicts (see forward()).  Works in fp64 when sd and inputs are fp64."""
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point
               and "running" not in k}
     cur = dict(sd)
     cur.update(params)
     outs = []
-    for x in (xa, xp, xn):                                    # train_triplet.py:215
+    for j, x in enumerate((xa, xp, xn)):                      # train_triplet.py:215
         st = {}
-        outs.append(forward(cur, x, True, st, storage=storage))
+        outs.append(forward(cur, x, True, st, storage=storage, masks=None if masks is None else masks[j],
+                            taps=None if taps is None else taps[j]))
         cur.update(st)                                        # running stats carry across the three calls
     loss = triplet_margin_loss(outs[0], outs[1], outs[2], margin)   # :219
     loss.backward()                                           # :223

@@ -75,3 +75,29 @@ def test_borrower_rejects_own_weights_and_training(model):
     e0.sync_weights(True)
     rc = e1.lib.dsk_load_weights(e1.handle, ctypes.byref(e0._wstruct), L.cur_stream())
     assert rc != 0 and b"borrows" in e1.lib.dsk_last_error()
+
+
+def test_shape_change_mid_stream_keeps_earlier_batches_intact(model):
+    """A ragged last batch (or any new (B, T)) re-zeroes the lane's padded workspace: that memset must be ordered after
+    the lane's forwards still in flight and before the new shape's kernels (it used to run on the NULL
+    stream, unordered against the non-blocking lane streams).  Many full batches are queued ahead of the short one so
+    that the host runs well ahead of the GPU, then shapes alternate."""
+    pipe = dsk.EmbeddingPipeline(model, lanes=2, depth=4)
+    full = [O.make_input(48, 160, seed=400 + i, scale=4.0) for i in range(10)]
+    short = [O.make_input(5, 160, seed=500 + i, scale=4.0) for i in range(3)]
+    seq = full[:8] + [short[0]] + full[8:] + [short[1], short[2], full[0]]
+    xh = [x.pin_memory() for x in seq]
+    oh = [torch.empty(x.shape[0], 512).pin_memory() for x in seq]
+    for i in range(len(seq)):
+        pipe.embed(xh[i], oh[i])
+    pipe.synchronize()
+    with torch.no_grad():
+        for i, x in enumerate(seq):
+            assert torch.equal(oh[i], model(x.cuda()).cpu()), i
+    # device entry point: the caller drops its input right away (record_stream keeps the block alive for the lane)
+    with torch.no_grad():
+        outs = [pipe.embed_device(x.cuda()) for x in seq]
+        pipe.synchronize()
+        torch.cuda.synchronize()
+        for i, x in enumerate(seq):
+            assert torch.equal(outs[i], model(x.cuda())), i

@@ -161,7 +161,7 @@ def test_branch_b_step_matches_reference_golden(cuda_dev, golden_dir):
     triplet = dsk.TripletMarginLoss(float(margin)).forward(sel(out_a), sel(out_p), sel(out_n))   # :275
     cls = [m.forward_classifier(x[h].contiguous()) for x in (xa, xp, xn)]               # :277-279
     true = torch.cat([label_p[h], label_p[h], label_n[h]])                               # :283
-    ce = torch.nn.CrossEntropyLoss()(torch.cat(cls), true)                               # :281-285
+    ce = dsk.CrossEntropyLoss()(torch.cat(cls), true)                                    # :281-285 (repo kernels)
     loss = ce + triplet * 2.0                                                            # :287
     m.zero_grad()
     loss.backward()                                                                      # :289-290
@@ -178,3 +178,44 @@ def test_branch_b_step_matches_reference_golden(cuda_dev, golden_dir):
         assert abs(p.grad.double().norm().item() - ref_norm) <= 0.15 * ref_norm + 1e-9, (kname, p.grad.norm().item(), ref_norm)
         checked += 1
     assert checked == 40 and m.model.classifier.weight.grad is not None
+
+
+def test_branch_b_step_b16_matches_reference_golden(cuda_dev, golden_dir):
+    """The well-conditioned branch-B fixture (16 triplets, T=160, 7 selected): classifier logits, cross-entropy and the
+    classifier gradients through the repo's own GEMM / log-softmax kernels at the north star's 1e-3."""
+    g = np.load(os.path.join(golden_dir, "branch_b_step_b16.npz"))
+    B, T, s0, s1, s2, scale, lseed, margin = g["cfg"]
+    sd = O.make_state_dict(0, 16)
+    m = make_model(sd, "fp16", cuda_dev)
+    xa, xp, xn = (O.make_input(int(B), int(T), int(s), float(scale)).cuda() for s in (s0, s1, s2))
+    label_p, label_n = torch.from_numpy(g["label_p"]).cuda(), torch.from_numpy(g["label_n"]).cuda()
+    out_a, out_p, out_n = m(xa), m(xp), m(xn)                                            # :215
+    l2 = dsk.PairwiseDistance(2)
+    d_p, d_n = l2.forward(out_a, out_p), l2.forward(out_a, out_n)                        # :251-252
+    idx, cnt = dsk.select_hard_triplets(d_p, d_n, float(margin))                         # :253-262
+    k = int(cnt.item())
+    assert len(set(idx[:k].tolist()) ^ set(g["hard"].tolist())) <= 2                     # margin = median of d_n - d_p
+    h = torch.from_numpy(g["hard"]).cuda()
+    sel = lambda t: t.detach()[h]
+    triplet = dsk.TripletMarginLoss(float(margin)).forward(sel(out_a), sel(out_p), sel(out_n))   # :275
+    cls = torch.cat([m.forward_classifier(x[h].contiguous()) for x in (xa, xp, xn)])    # :277-279
+    true = torch.cat([label_p[h], label_p[h], label_n[h]])                               # :283
+    ce = dsk.CrossEntropyLoss()(cls, true)                                               # :281-285
+    loss = ce + triplet * 2.0                                                            # :287
+    m.zero_grad()
+    loss.backward()                                                                      # :289-290
+    ref_logits = torch.from_numpy(g["logits"])
+    assert (cls.detach().cpu() - ref_logits).abs().max().item() <= 2e-3 * ref_logits.abs().max().item()
+    assert abs(ce.item() - float(g["ce"])) <= 1e-3 * float(g["ce"])
+    assert abs(triplet.item() - float(g["triplet"])) <= 2e-3 * 10.0      # distances are O(10): 1e-3 relative to them
+    for kname in ("model.classifier.weight", "model.classifier.bias"):
+        got, ref = dict(m.named_parameters())[kname].grad.cpu(), torch.from_numpy(g["gfull/" + kname])
+        assert rel_l2(got, ref) < 5e-3, (kname, rel_l2(got, ref))
+    checked = 0
+    for kname, p in m.named_parameters():
+        if "gnorm/" + kname not in g:
+            continue
+        ref_norm = float(g["gnorm/" + kname])
+        assert abs(p.grad.double().norm().item() - ref_norm) <= 0.05 * ref_norm + 1e-9, (kname, p.grad.norm().item(), ref_norm)
+        checked += 1
+    assert checked == 40

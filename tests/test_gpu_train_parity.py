@@ -1,0 +1,147 @@
+"""Training-path parity proper: the CUDA branch-A step (train_triplet.py:215-224) against the
+oracle with the clip pass-through sets pinned, at batch sizes up to BASELINE configs[2] (128 triplets), plus
+bit-reproducibility of the gradients and a 20-step Adagrad loss trajectory.
+
+Why masks are pinned.  Hardtanh(0,20) (model.py:36-39) has a discontinuous gradient.  An element whose pre-activation
+lies within rounding distance of 0 or 20 passes the gradient in one implementation and blocks it in the other, and ONE
+such flip moves every upstream gradient by ~1/sqrt(#elements of the layer): the fp32 and fp64 runs of the oracle itself
+differ by 2.5e-3 rel-L2 on all tensors below such an element at batch 6 (test_oracle_fp32_vs_fp64_gradient_noise in
+tests/test_oracle_golden.py).  16-bit activation storage moves ~4e-4 of the elements across a boundary, hence the
+2-10 % end-to-end gradient rel-L2 of tests/test_gpu_train.py, which says nothing about kernel correctness.  Here the
+oracle differentiates through exactly the elements the engine passed (read back from the train context with
+dsk_train_ctx_read), so every remaining difference is arithmetic: operand rounding and summation order.
+"""
+import ctypes
+
+import pytest
+import torch
+
+import deepspeaker_pytorch_b200 as dsk
+from deepspeaker_pytorch_b200 import _lib as L
+from oracle import rescnn_oracle as O
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def make_model(sd, dt, dev):
+    m = dsk.DeepSpeakerModel(512, 16, operand_dtype=dt).to(dev)
+    m.load_state_dict(sd)
+    return m.train()
+
+
+def read_saved_activations(m, emb, T):
+    """Post-activation tensors y[0..11] (fp32 NCHW) a train-mode forward saved, through the C ABI debug read."""
+    eng, tctx = m._engine, emb.grad_fn.guard.tctx
+    B = emb.shape[0]
+    out = {}
+    for i in range(12):
+        st = i // 3
+        t = torch.empty(B, 64 << st, T >> (st + 1), 64 >> (st + 1), device=emb.device, dtype=torch.float32)
+        L.check(eng.lib.dsk_train_ctx_read(eng.handle, tctx, 1, i, t.data_ptr(), L.cur_stream()), "dsk_train_ctx_read")
+        out[i] = t
+    return out
+
+
+def engine_step(m, xs, T, margin=0.1):
+    outs = [m(x) for x in xs]                                                # train_triplet.py:215
+    acts = [read_saved_activations(m, o, T) for o in outs]
+    masks = [{i: ((y > 0) & (y < 20)).cpu() for i, y in a.items()} for a in acts]
+    loss = dsk.TripletMarginLoss(margin).forward(*outs)                      # :219
+    m.zero_grad()
+    loss.backward()                                                          # :223
+    grads = {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters() if p.grad is not None}
+    return loss.detach().cpu(), [o.detach().cpu() for o in outs], masks, grads
+
+
+def oracle_step(sd, xs, margin, masks, storage, f64):
+    if f64:
+        sd = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+        xs = [x.double() for x in xs]
+    taps = [{}, {}, {}]
+    loss, grads, oa, op, on = O.triplet_step_branch_a(sd, *xs, margin, storage=storage, masks=masks, taps=taps)
+    own = [{i: ((t[i] > 0) & (t[i] < 20)) for i in t} for t in taps]
+    return loss, grads, (oa, op, on), own
+
+
+# (B, T, max grad rel-L2 against the mask-pinned storage-matched oracle, embedding rel)
+CASES = [(6, 160, 4e-3, 1.5e-3), (16, 48, 4e-3, 3e-3), (128, 160, 4e-3, 1.5e-3)]
+
+
+@pytest.mark.parametrize("B,T,gtol,etol", CASES)
+def test_fp16_step_matches_mask_pinned_oracle(cuda_dev, B, T, gtol, etol):
+    """Production fp16 path.  The oracle rounds what the engine stores in 16 bit (storage=float16) and differentiates
+    through the engine's own clip masks: what is left is the fp16 rounding of the stored gradient tensors and fp32
+    summation order.  B=128, T=160 is BASELINE configs[2]."""
+    sd = O.make_state_dict(1, 16)
+    m = make_model(sd, "fp16", cuda_dev)
+    xs = [O.make_input(B, T, s, 3.0) for s in (20, 21, 22)]
+    loss, outs, masks, grads = engine_step(m, [x.cuda() for x in xs], T)
+    oloss, ograds, oouts, own = oracle_step(sd, xs, 0.1, masks, torch.float16, f64=False)
+    flips = sum(int((masks[j][i] != own[j][i]).sum()) for j in range(3) for i in range(12))
+    total = sum(masks[j][i].numel() for j in range(3) for i in range(12))
+    erel = max(float(((outs[j] - oouts[j]).norm(dim=1) / oouts[j].norm(dim=1)).max()) for j in range(3))
+    worst = max((rel_l2(grads[k], ograds[k]), k) for k in grads)
+    print(f"B={B} T={T}: emb rel {erel:.2e}, loss {loss.item():.6f} vs {oloss.item():.6f}, clip-mask flips {flips}/{total}, "
+          f"worst grad rel-L2 {worst[0]:.2e} ({worst[1]})")
+    assert erel < etol
+    assert abs(loss.item() - oloss.item()) <= 2e-3 * max(abs(oloss.item()), 0.05)
+    assert len(grads) == 38
+    for k in grads:
+        assert rel_l2(grads[k], ograds[k]) < gtol, (k, rel_l2(grads[k], ograds[k]))
+
+
+def test_gradients_are_bit_reproducible(cuda_dev):
+    """Split-K weight gradients are reduced in fixed order (no atomics): two runs of the same step give the same bits."""
+    sd = O.make_state_dict(2, 16)
+    xs = [O.make_input(8, 160, s, 3.0).cuda() for s in (1, 2, 3)]
+    runs = []
+    for _ in range(2):
+        m = make_model(sd, "fp16", cuda_dev)
+        loss, outs, _, grads = engine_step(m, xs, 160)
+        runs.append((loss, outs, grads))
+    assert torch.equal(runs[0][0], runs[1][0])
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert torch.equal(a, b)
+    for k in runs[0][2]:
+        assert torch.equal(runs[0][2][k], runs[1][2][k]), k
+
+
+def test_adagrad_loss_trajectory_follows_the_oracle(cuda_dev):
+    """20 branch-A steps with the fused Adagrad (train_triplet.py:215-224 + :369-383) against the oracle stepped by
+    torch.optim.Adagrad on the CPU.  lr is 100x below the reference default so that the comparison measures the
+    implementation and not the chaos of lr=0.1 steps on an untrained net."""
+    B, T, steps, lr = 8, 64, 20, 1e-3
+    sd = O.make_state_dict(3, 16)
+    m = make_model(sd, "fp16", cuda_dev)
+    opt = dsk.FusedAdagrad(m.parameters(), lr=lr, lr_decay=1e-4, weight_decay=0.0)
+    crit = dsk.TripletMarginLoss(0.5)
+    cur = {k: v.clone() for k, v in sd.items()}
+    params = {k: v.requires_grad_(True) for k, v in cur.items() if v.dtype.is_floating_point and "running" not in k}
+    oopt = torch.optim.Adagrad(list(params.values()), lr=lr, lr_decay=1e-4, weight_decay=0.0)
+    ours, ref = [], []
+    for it in range(steps):
+        xs = [O.make_input(B, T, 100 + 3 * it + j, 3.0) for j in range(3)]
+        out = [m(x.cuda()) for x in xs]
+        loss = crit.forward(*out)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ours.append(loss.item())
+        outs = []
+        for x in xs:
+            st = {}
+            outs.append(O.forward(cur, x, True, st))
+            cur.update(st)
+        oloss = O.triplet_margin_loss(*outs, 0.5)
+        oopt.zero_grad()
+        oloss.backward()
+        oopt.step()
+        ref.append(oloss.item())
+    dev = max(abs(a - b) / max(abs(b), 1e-3) for a, b in zip(ours, ref))
+    print("loss trajectory ours:", [round(v, 4) for v in ours], "\n              oracle:", [round(v, 4) for v in ref], f"\nmax rel dev {dev:.3e}")
+    assert dev < 2e-2
+    for k, p in m.named_parameters():   # parameters after 20 steps
+        if "classifier" in k:
+            continue
+        assert rel_l2(p.detach().cpu(), cur[k].detach()) < 2e-2, k

@@ -3,6 +3,7 @@ reference's own model.py (tools/make_golden.py).  CPU only."""
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import c_oracle as C
@@ -122,9 +123,10 @@ def test_allpairs_matches_reference_distance(golden_dir):
     assert (i2 == idx).mean() > 0.98
 
 
-def test_branch_b_step_matches_reference(golden_dir):
+@pytest.mark.parametrize("name", ["branch_b_step.npz", "branch_b_step_b16.npz"])
+def test_branch_b_step_matches_reference(golden_dir, name):
     """Selection -> forward_classifier -> cross-entropy step, train_triplet.py:251-291."""
-    g = np.load(os.path.join(golden_dir, "branch_b_step.npz"))
+    g = np.load(os.path.join(golden_dir, name))
     B, T, s0, s1, s2, scale, lseed, margin = g["cfg"]
     sd = O.make_state_dict(0, 16)
     xa, xp, xn = (O.make_input(int(B), int(T), int(s), float(scale)) for s in (s0, s1, s2))
@@ -140,3 +142,37 @@ def test_branch_b_step_matches_reference(golden_dir):
         assert abs(gr.double().norm().item() - ref_norm) <= 2e-3 * ref_norm + 1e-7, k
         n += 1
     assert n == 40        # the classifier now receives gradients too
+
+
+def test_adagrad_golden_is_the_reference_update_rule(golden_dir):
+    """tests/golden/adagrad.npz (torch.optim.Adagrad, the optimizer train_triplet.py:369-383 builds) follows
+    G += g^2; p -= lr/(1+(t-1)*lr_decay) * g / (sqrt(G) + 1e-10): the rule csrc/head_kernels.cuh fuses."""
+    g = np.load(os.path.join(golden_dir, "adagrad.npz"))
+    p, G = g["p0"].astype(np.float64), 0.0
+    for t, gr in enumerate(g["grads"].astype(np.float64), start=1):
+        G = G + gr * gr
+        p = p - float(g["lr"]) / (1 + (t - 1) * float(g["lr_decay"])) * gr / (np.sqrt(G) + 1e-10)
+    assert np.allclose(p, g["p_final"], rtol=1e-5, atol=1e-7)
+    assert np.allclose(G, g["sum_final"], rtol=1e-5)
+
+
+def test_oracle_fp32_vs_fp64_gradient_noise():
+    """Documents why the GPU gradient tests pin the clip masks: the oracle's own fp32 and fp64 runs agree to ~1e-6 on
+    embeddings, and on every gradient whose backward path crosses no flipped clip element; one flipped element
+    (a pre-activation within 1e-7 of 0 or 20) moves all upstream gradients by ~1/sqrt(#elements).  With the masks of
+    the fp64 run forced on the fp32 run, all 38 gradients agree to fp32 round-off."""
+    B, T = 6, 160
+    sd = O.make_state_dict(1, 16)
+    xs = [O.make_input(B, T, s, 3.0) for s in (20, 21, 22)]
+    sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    taps = [{}, {}, {}]
+    l64, g64, a64, _, _ = O.triplet_step_branch_a(sd64, *[x.double() for x in xs], 0.1, taps=taps)
+    masks = [{i: ((t[i] > 0) & (t[i] < 20)).detach() for i in t} for t in taps]
+    l32, g32, a32, _, _ = O.triplet_step_branch_a(sd, *xs, 0.1)
+    l32m, g32m, _, _, _ = O.triplet_step_branch_a(sd, *xs, 0.1, masks=masks)
+    assert ((a32.double() - a64).norm(dim=1) / a64.norm(dim=1)).max().item() < 1e-5
+    free = max(((g32[k].double() - g64[k]).norm() / g64[k].norm()).item() for k in g64 if g64[k] is not None)
+    pinned = max(((g32m[k].double() - g64[k]).norm() / g64[k].norm()).item() for k in g64 if g64[k] is not None)
+    print(f"worst gradient rel-L2 fp32 vs fp64: free masks {free:.2e}, pinned masks {pinned:.2e}")
+    assert pinned < 5e-5
+    assert free < 2e-2   # typically 2.5e-3: one flip; bounded loosely, the point is `pinned`

@@ -118,13 +118,14 @@ def golden_train():
     print("train_step.npz: loss", loss.item(), "params with grad", sum(1 for k in out if k.startswith("gnorm/")))
 
 
-def golden_branch_b():
-    """Branch-B step (train_triplet.py:215,251-291) with the reference model and its own forward_classifier."""
+def golden_branch_b(B=6, T=32, seeds=(30, 31, 32), name="branch_b_step.npz", full_head=False):
+    """Branch-B step (train_triplet.py:215,251-291) with the reference model and its own forward_classifier.
+    The (B=6, T=32) fixture selects 2-3 utterances (BatchNorm over 16 values per channel at stage 4: the most
+    ill-conditioned shape the path can see); the (B=16, T=160) one is the well-conditioned case the 1e-3 gates use."""
     import torch.nn as nn
     sd = O.make_state_dict(0, NUM_CLASSES)
     m = ref_model(sd).train()
-    B, T = 6, 32
-    xa, xp, xn = (O.make_input(B, T, s, 3.0) for s in (30, 31, 32))
+    xa, xp, xn = (O.make_input(B, T, s, 3.0) for s in seeds)
     g = torch.Generator().manual_seed(33)
     label_p = torch.randint(0, NUM_CLASSES, (B,), generator=g)
     label_n = torch.randint(0, NUM_CLASSES, (B,), generator=g)
@@ -143,7 +144,7 @@ def golden_branch_b():
     loss = ce + triplet * 2.0                                                   # :287
     m.zero_grad()
     loss.backward()                                                             # :289-290
-    out = {"cfg": np.array([B, T, 30, 31, 32, 3.0, 33, margin]), "hard": hard.astype(np.int64),
+    out = {"cfg": np.array([B, T, seeds[0], seeds[1], seeds[2], 3.0, 33, margin]), "hard": hard.astype(np.int64),
            "triplet": np.array(triplet.item(), np.float32), "ce": np.array(ce.item(), np.float32),
            "loss": np.array(loss.item(), np.float32), "label_p": label_p.numpy(), "label_n": label_n.numpy()}
     for k, v in m.named_parameters():
@@ -154,8 +155,12 @@ def golden_branch_b():
         out["gnorm/" + k] = np.array(gflat.double().norm().item())
         out["gidx/" + k] = ix
         out["gval/" + k] = gflat[ix].numpy()
-    np.savez(os.path.join(OUT, "branch_b_step.npz"), **out)
-    print("branch_b_step.npz: selected", len(hard), "of", B, "ce", ce.item(), "triplet", triplet.item(),
+        if full_head and "classifier" in k:
+            out["gfull/" + k] = v.grad.numpy()
+    if full_head:
+        out["logits"] = torch.cat([cls_a, cls_p, cls_n]).detach().numpy()
+    np.savez(os.path.join(OUT, name), **out)
+    print(name, ": selected", len(hard), "of", B, "ce", ce.item(), "triplet", triplet.item(),
           "params with grad", sum(1 for k in out if k.startswith("gnorm/")))
 
 
@@ -187,6 +192,23 @@ def golden_verification():
     print("verification.npz: accuracy", acc, "tpr", tpr, "fpr", fpr)
 
 
+def golden_adagrad():
+    """torch.optim.Adagrad with the reference's hyper-parameters (train_triplet.py:70-77,378-382) on the CPU."""
+    g = torch.Generator().manual_seed(77)
+    p = torch.nn.Parameter(torch.randn(4099, generator=g) * 0.05)
+    p0 = p.detach().clone().numpy()
+    opt = torch.optim.Adagrad([p], lr=0.1, lr_decay=1e-4, weight_decay=0.0)
+    grads = []
+    for it in range(6):
+        gr = torch.randn(4099, generator=g) * 10.0 ** (-(it % 3))
+        grads.append(gr.numpy())
+        p.grad = gr.clone()
+        opt.step()
+    np.savez(os.path.join(OUT, "adagrad.npz"), p0=p0, grads=np.stack(grads), p_final=p.detach().numpy(),
+             sum_final=opt.state[p]["sum"].numpy(), lr=np.array(0.1), lr_decay=np.array(1e-4))
+    print("adagrad.npz: |p_final - p0| max", float(np.abs(p.detach().numpy() - p0).max()))
+
+
 def golden_keys():
     import json
     m = R.DeepSpeakerModel(512, NUM_CLASSES)
@@ -197,11 +219,18 @@ def golden_keys():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":   # only the fixtures added in round 2 (the others are unchanged)
+        torch.set_num_threads(8)
+        golden_adagrad()
+        golden_branch_b(16, 160, (40, 41, 42), "branch_b_step_b16.npz", True)
+        sys.exit(0)
     golden_keys()
     torch.set_num_threads(8)
     golden_eval()
     golden_loss()
     golden_train()
     golden_branch_b()
+    golden_branch_b(16, 160, (40, 41, 42), "branch_b_step_b16.npz", True)
+    golden_adagrad()
     golden_verification()
     golden_allpairs()
