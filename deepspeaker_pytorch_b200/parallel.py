@@ -22,7 +22,9 @@ class GradBucket:
             raise ValueError("GradBucket needs at least one parameter")
         dev = self.params[0].device
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        # one extra slot after the gradients carries the rank's weight through the same collective (weighted mean)
+        self._ext = torch.zeros(self.numel + 1, dtype=torch.float32, device=dev)
+        self.flat = self._ext[:self.numel]
         self.group = process_group
         off = 0
         for p in self.params:
@@ -47,6 +49,21 @@ class GradBucket:
         self.flat.div_(world)
         self.collectives += 1
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+
+    def allreduce_weighted_mean(self, weight):
+        """Hard-triplet branch (train_triplet.py:262-291): rank r holds the gradient of the MEAN loss over its own k_r
+        selected triplets, and k_r differs per rank.  The gradient of the mean over the global selection is
+        sum_r k_r g_r / sum_r k_r: the bucket is scaled by k_r, k_r itself rides in the extra slot of the same buffer,
+        and ONE sum-allreduce delivers numerator and denominator together.  ``weight``: python number or
+        0-d tensor (stays on the device: no host synchronisation).  A rank with k_r = 0 contributes zeros."""
+        w = torch.as_tensor(weight, dtype=torch.float32, device=self.flat.device).reshape(())
+        self.flat.mul_(w)
+        self._ext[self.numel] = w
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self.collectives += 1
+            dist.all_reduce(self._ext, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.div_(self._ext[self.numel].clamp_min(1e-30))
+        return self._ext[self.numel]
 
 
 def path_parameters(module):

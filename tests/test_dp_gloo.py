@@ -65,6 +65,38 @@ def test_single_allreduce_matches_global_batch_gradient():
     assert torch.allclose(flat0, torch.cat([w.grad.flatten(), b.grad.flatten()]), atol=1e-6)
 
 
+def _worker_weighted(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = torch.nn.Parameter(torch.ones(6, 3))
+    b = torch.nn.Parameter(torch.zeros(3))
+    bucket = GradBucket([w, b])
+    x_global = torch.randn(8, 6, generator=torch.Generator().manual_seed(7))
+    rows = (x_global[:5], x_global[5:])[rank]           # rank 0 selected 5 "hard triplets", rank 1 selected 3
+    bucket.zero()
+    _toy_loss(w, b, rows).backward()                    # local MEAN over the rank's own selection
+    total = bucket.allreduce_weighted_mean(float(rows.shape[0]))
+    out[rank] = (bucket.flat.clone(), float(total), bucket.collectives)
+    dist.destroy_process_group()
+
+
+def test_weighted_allreduce_is_the_mean_over_the_global_selection():
+    """Branch B under data parallelism: k_r differs per rank; one collective carries gradients and weights."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_weighted, args=(world, port, out), nprocs=world, join=True)
+    (flat0, tot0, n0), (flat1, tot1, n1) = out[0], out[1]
+    assert tot0 == 8.0 and tot1 == 8.0 and n0 == 1 and n1 == 1
+    assert torch.allclose(flat0, flat1)
+    w = torch.ones(6, 3, requires_grad=True)
+    b = torch.zeros(3, requires_grad=True)
+    x_global = torch.randn(8, 6, generator=torch.Generator().manual_seed(7))
+    _toy_loss(w, b, x_global).backward()                # mean over all 8 selected rows
+    assert torch.allclose(flat0, torch.cat([w.grad.flatten(), b.grad.flatten()]), atol=1e-6)
+
+
 def test_bucket_covers_the_triplet_path_parameters():
     m = DeepSpeakerModel(512, 1211)
     ps = path_parameters(m)
