@@ -18,6 +18,7 @@
 #include "conv1_umma.cuh"
 #include "head_kernels.cuh"
 #include "loss_kernels.cuh"
+#include "metric_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "train_kernels.cuh"
 #include "wgrad_umma.cuh"
@@ -2075,6 +2076,17 @@ int32_t dsk_adagrad_step(float* param, const float* grad, float* state_sum, int6
   dsk::adagrad_flat_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, grad, state_sum, n, grad_mult, grad_denom, static_cast<float>(minus_clr), static_cast<float>(eps),
       static_cast<float>(weight_decay));
+  KERNEL_CHECK();
+  return DSK_OK;
+}
+
+int32_t dsk_threshold_counts(const float* dist, const uint8_t* same, int32_t P, const double* thresholds, int32_t nT,
+                             int32_t* tp, int32_t* fp, void* stream) {
+  if (!dist || !same || !thresholds || !tp || !fp || P <= 0 || nT <= 0)
+    return fail(DSK_ERR_INVALID, "dsk_threshold_counts: bad arguments");
+  const int blocks = (nT + dsk::kSweepThreads - 1) / dsk::kSweepThreads;
+  dsk::threshold_counts_kernel<<<blocks, dsk::kSweepThreads, 0, static_cast<cudaStream_t>(stream)>>>(dist, same, P, thresholds,
+                                                                                                      nT, tp, fp);
   KERNEL_CHECK();
   return DSK_OK;
 }

@@ -237,6 +237,14 @@ int32_t dsk_adagrad_step(float* param, const float* grad, float* state_sum, int6
                          double weight_decay, double eps, int64_t step, float grad_mult, const float* grad_denom,
                          void* stream);
 
+/* Threshold sweep of the verification metric (/root/reference/eval_metrics.py:16-37 calculate_roc, :53-88 calculate_val /
+ * calculate_val_far; called from train_triplet.py:361): for every threshold t (double, as numpy's arange yields them)
+ * tp[t] = #{i : same[i] && (double)dist[i] < t}, fp[t] = #{i : !same[i] && (double)dist[i] < t} — numpy's
+ * np.less(dist, t) with its float32 -> float64 promotion, so the counts are exactly the reference's.  All other sweep
+ * quantities (tn, fn, tpr, fpr, accuracy, val, far) are integer arithmetic on tp, fp, n_same, n_diff. */
+int32_t dsk_threshold_counts(const float* dist, const uint8_t* same, int32_t P, const double* thresholds, int32_t nT,
+                             int32_t* tp, int32_t* fp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

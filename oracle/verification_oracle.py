@@ -53,3 +53,33 @@ def equal_error_rate(distances, labels, thresholds=None):
     # linear interpolation between the bracketing thresholds
     w = -diff[i - 1] / (diff[i] - diff[i - 1]) if diff[i] != diff[i - 1] else 0.0
     return float((far[i - 1] + w * (far[i] - far[i - 1]) + frr[i - 1] + w * (frr[i] - frr[i - 1])) / 2)
+
+
+def calculate_val_far(threshold, dist, actual_issame):
+    """eval_metrics.py:75-88"""
+    predict_issame = np.less(dist, threshold)
+    true_accept = np.sum(np.logical_and(predict_issame, actual_issame))
+    false_accept = np.sum(np.logical_and(predict_issame, np.logical_not(actual_issame)))
+    n_same = np.sum(actual_issame)
+    n_diff = np.sum(np.logical_not(actual_issame))
+    if n_diff == 0:
+        n_diff = 1
+    if n_same == 0:
+        return 0, 0
+    return float(true_accept) / float(n_same), float(false_accept) / float(n_diff)
+
+
+def calculate_val(thresholds, distances, labels, far_target=0.1):
+    """eval_metrics.py:53-73.  The reference's scipy interp1d('slinear') call raises on the duplicate FAR values of any
+    real curve under current scipy (tools/make_golden.py records the failure), so the crossing threshold is pinned on
+    the de-duplicated curve, where 'slinear' is plain linear interpolation: the golden `val_threshold_dedup` is produced
+    by the reference's OWN interp1d call on that curve."""
+    far_train = np.array([calculate_val_far(t, distances, labels)[1] for t in thresholds])
+    if np.max(far_train) >= far_target:
+        keep = np.concatenate(([True], np.diff(far_train) > 0))
+        x, y = far_train[keep], thresholds[keep]
+        threshold = float(y[0]) if far_target <= x[0] else float(np.interp(far_target, x, y))
+    else:
+        threshold = 0.0
+    val, far = calculate_val_far(threshold, distances, labels)
+    return val, far, threshold

@@ -53,3 +53,43 @@ def test_heldout_eer_within_a_tenth_of_a_percent(cuda_dev):
     assert 0.0 <= eer_r < 0.5
     assert abs(eer_g - eer_r) <= 1e-3, (eer_g, eer_r)          # north star: within 0.1 % absolute
     assert abs(acc_g - acc_r) <= 1.0 / P + 1e-9
+
+
+def test_oracle_val_at_far_matches_reference_ingredients(golden_dir):
+    """VAL@FAR (eval_metrics.py:53-88): the oracle against the golden made from the reference's own calculate_val_far and
+    scipy interp1d('slinear') on the de-duplicated FAR curve (the reference's calculate_val itself raises on duplicates)."""
+    g = np.load(os.path.join(golden_dir, "verification.npz"))
+    assert "duplicates" in str(g["ref_calculate_val_raises"])
+    th = np.arange(0, 30, 0.001)
+    for name, target in (("1e-2", 1e-2), ("5e-2", 5e-2)):
+        val, far, thr = VO.calculate_val(th, g["distances"], g["labels"], target)
+        assert abs(thr - float(g[f"val_threshold_{name}"])) < 1e-9
+        assert val == float(g[f"val_{name}"]) and far == float(g[f"far_{name}"])
+
+
+@pytest.mark.gpu
+def test_gpu_evaluate_matches_reference_eval_metrics(cuda_dev, golden_dir):
+    """verification.evaluate = eval_metrics.evaluate with the sweeps counted on the GPU: identical counts, so identical
+    tpr / fpr / accuracy (reference golden) and VAL / FAR (golden + oracle)."""
+    g = np.load(os.path.join(golden_dir, "verification.npz"))
+    d = torch.from_numpy(g["distances"]).float().to(cuda_dev)
+    lab = torch.from_numpy(g["labels"]).to(cuda_dev)
+    d64 = d.cpu().numpy().astype(np.float64)          # the fp32 distances the GPU sees, as numpy would promote them
+    th = np.arange(0, 30, 0.01)
+    tp, fp = V.threshold_counts(d, lab, th)
+    same = g["labels"].astype(bool)
+    assert np.array_equal(tp, [(np.less(d64, t) & same).sum() for t in th])
+    assert np.array_equal(fp, [(np.less(d64, t) & ~same).sum() for t in th])
+    for target, name in ((1e-2, "1e-2"), (5e-2, "5e-2")):
+        tpr, fpr, acc, val, far = V.evaluate(d, lab, far_target=target)
+        otpr, ofpr, oacc = VO.evaluate_accuracy(d64, same)
+        assert (tpr, fpr, acc) == (otpr, ofpr, oacc)
+        assert abs(acc - float(g["ref_accuracy"])) < 1e-12 and abs(tpr - float(g["ref_tpr"])) < 1e-12
+        oval, ofar, _ = VO.calculate_val(np.arange(0, 30, 0.001), d64, same, target)
+        assert (val, far) == (oval, ofar)
+        assert abs(val - float(g[f"val_{name}"])) < 1e-12 and abs(far - float(g[f"far_{name}"])) < 1e-12
+    # degenerate inputs: no same-speaker pair -> (0, 0) as calculate_val_far returns; FAR never reaches the target -> threshold 0
+    z = V.evaluate(d, torch.zeros_like(lab), far_target=1e-3)
+    assert z[3] == 0.0 and z[4] == 0.0
+    with pytest.raises(RuntimeError):
+        V.threshold_counts(d.cpu(), lab.cpu(), th)

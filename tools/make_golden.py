@@ -184,12 +184,30 @@ def golden_verification():
     g = np.random.RandomState(7)
     labels = (np.arange(400) % 2 == 0)
     distances = np.where(labels, g.normal(9.0, 2.0, 400), g.normal(13.0, 2.0, 400)).astype(np.float64)
-    # evaluate()'s VAL@FAR half (eval_metrics.py:10-12) raises under current scipy (interp1d on a FAR curve with
-    # duplicate x values); the accuracy half (:7-9 -> calculate_roc) is the part pinned here
     tpr, fpr, acc = EM.calculate_roc(np.arange(0, 30, 0.01), distances, labels)
+    # evaluate()'s VAL@FAR half (eval_metrics.py:10-12) raises under current scipy (interp1d on a FAR curve with
+    # duplicate x values): record that, and pin the crossing threshold with the reference's own ingredients —
+    # calculate_val_far for the curve and scipy's interp1d('slinear') on the de-duplicated curve
+    from scipy import interpolate
+    th2 = np.arange(0, 30, 0.001)
+    try:
+        EM.calculate_val(th2, distances, labels, 1e-2)
+        raised = ""
+    except Exception as e:  # noqa: BLE001
+        raised = type(e).__name__ + ": " + str(e)[:120]
+    far_train = np.array([EM.calculate_val_far(t, distances, labels)[1] for t in th2])
+    out = {}
+    for name, target in (("1e-2", 1e-2), ("5e-2", 5e-2)):
+        keep = np.concatenate(([True], np.diff(far_train) > 0))
+        f = interpolate.interp1d(far_train[keep], th2[keep], kind="slinear")
+        thr = float(f(target))
+        val, far = EM.calculate_val_far(thr, distances, labels)
+        out[f"val_threshold_{name}"] = np.array(thr)
+        out[f"val_{name}"] = np.array(val)
+        out[f"far_{name}"] = np.array(far)
     np.savez(os.path.join(OUT, "verification.npz"), distances=distances, labels=labels, ref_tpr=np.array(tpr),
-             ref_fpr=np.array(fpr), ref_accuracy=np.array(acc))
-    print("verification.npz: accuracy", acc, "tpr", tpr, "fpr", fpr)
+             ref_fpr=np.array(fpr), ref_accuracy=np.array(acc), ref_calculate_val_raises=np.array(raised), **out)
+    print("verification.npz: accuracy", acc, "tpr", tpr, "fpr", fpr, "| calculate_val raised:", raised or "no", "|", {k: float(v) for k, v in out.items()})
 
 
 def golden_adagrad():
