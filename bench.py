@@ -544,8 +544,9 @@ TRAIN_FLOP_PER_UTT = 6911819776     # BASELINE.md §2 (forward + backward)
 
 def bench_train(args, D):
     """BASELINE configs[2] (N=1) / configs[4] (N=8): triplet training step restating train_triplet.py:215-224 with the
-    drop-in classes — three train-mode forwards of 128 utterances, TripletMarginLoss, backward, ONE gradient allreduce
-    over the flat bucket (N > 1, NCCL over NVLink), fused Adagrad step (train_triplet.py:369-383)."""
+    drop-in classes — three train-mode forwards of 128 utterances (issued together through forward_triplet: identical
+    results, the three calls and their backwards overlap on three streams), TripletMarginLoss, backward, ONE gradient
+    allreduce over the flat bucket (N > 1, NCCL over NVLink), fused Adagrad step (train_triplet.py:369-383)."""
     import torch
 
     from deepspeaker_pytorch_b200 import FusedAdagrad, TripletMarginLoss
@@ -564,7 +565,7 @@ def bench_train(args, D):
     xs = [tuple(torch.randn(B, 1, T, 64, device=dev, generator=g) for _ in range(3)) for _ in range(nset)]
 
     def step(xa, xp, xn):
-        out_a, out_p, out_n = model(xa), model(xp), model(xn)       # :215
+        out_a, out_p, out_n = model.forward_triplet(xa, xp, xn)     # :215, the three calls in flight together
         loss = crit.forward(out_a, out_p, out_n)                    # :219
         opt.zero_grad()                                             # :222
         loss.backward()                                             # :223

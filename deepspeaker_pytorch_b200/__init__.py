@@ -7,5 +7,6 @@ from .model import (DeepSpeakerModel, PairwiseDistance, TripletMarginLoss, allpa
 from .pipeline import EmbeddingPipeline  # noqa: F401,E402
 from .head import CrossEntropyLoss  # noqa: F401,E402
 from .optim import FusedAdagrad  # noqa: F401,E402
+from .steps import train_step  # noqa: F401,E402
 
-__all__ = ["CrossEntropyLoss", "FusedAdagrad", "EmbeddingPipeline", "DeepSpeakerModel", "PairwiseDistance", "TripletMarginLoss", "select_hard_triplets", "allpairs_topk"]
+__all__ = ["train_step", "CrossEntropyLoss", "FusedAdagrad", "EmbeddingPipeline", "DeepSpeakerModel", "PairwiseDistance", "TripletMarginLoss", "select_hard_triplets", "allpairs_topk"]

@@ -162,6 +162,8 @@ SIGNATURES = {
     "dsk_cross_entropy_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "dsk_adagrad_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
                                    c_int64, c_float, c_void_p, c_void_p]),
+    "dsk_set_defer_running_stats": (c_int32, [c_void_p, c_int32]),
+    "dsk_train_ctx_commit_stats": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "dsk_threshold_counts": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -60,6 +60,8 @@ struct HaloParams {
   int late_trigger;       // release the dependent kernel when this CTA starts its last tile instead of at entry
   int b_resident;         // all weight boxes of a CTA's channel tile fit the B ring: load once
   unsigned pitch_magic, img_magic;  // floor(2^32/d)+1 for d = W+1 and H+1: q/d == __umulhi(q, magic) for q < 2^32/d
+  const uint16_t* res_ptr;  // residual tensor (padded layout, cout channels per position): read straight from global / L2
+                            // by the 4-epilogue-warp variant, which has no shared memory to spare for residual tiles
   long long* trace;       // debug: per-role clock64 stamps of CTA 0 (nullptr = off); [role 0..2][512]
 };
 
@@ -91,11 +93,22 @@ struct HaloPlan {
   }
 };
 
-template <int N_TILE>
+// Two CTA shapes of the same kernel (template parameter EW = epilogue warps):
+//   EW = 8: 384 threads, the whole SM (up to 227 KB of shared memory, 512 TMEM columns, 3-tap weight boxes);
+//   EW = 4: 256 threads, <= 128 registers, <= 112.5 KB of shared memory and 256 TMEM columns, so that TWO CTAs share
+//           an SM.  A layer of this network gives an SM only one or two tiles, and a CTA spends ~1.8 us before its
+//           first MMA (launch, barrier / TMEM set-up, first operand fetch) and ~2.8 us after its last one (epilogue of
+//           the last tile) with the tensor pipe idle (clock64 traces, profiles/r02_trace_halo.txt).  With two CTAs per
+//           SM - two tiles of one layer, the early-launched CTA of the next kernel of the chain, or a CTA of another
+//           forward in flight - one CTA's set-up and epilogue run under the other's MMAs.  Weight boxes shrink to one
+//           tap (16 KB at 128 channels), the residual is read straight from L2 instead of through a prefetched tile.
+template <int N_TILE, int EW = 8>
 struct HaloSmem {
-  static constexpr int kTapsPerBox = N_TILE == 256 ? 1 : 3;  // weight box: 3 taps (48 KB at 128 channels), 1 tap at 256
+  static constexpr bool kSmall = EW == 4;
+  static constexpr int kTapsPerBox = (N_TILE == 256 || kSmall) ? 1 : 3;  // weight box: 3 taps (48 KB at 128 channels) or 1
   static constexpr int kBStageBytes = kTapsPerBox * N_TILE * 128;
-  static constexpr int kAccStages = N_TILE == 256 ? 2 : 4;   // TMEM accumulators: kAccStages x N_TILE <= 512 columns
+  static constexpr int kTmemCols = kSmall ? 256 : (N_TILE == 256 ? 512 : 4 * N_TILE);
+  static constexpr int kAccStages = kTmemCols / N_TILE;      // TMEM accumulators
   static constexpr int kRowDstBytes = 2 * 128 * 8;                  // planar output: per-row destination, two tiles
   static constexpr int kFixedBytes = kRowDstBytes + 512 + 1024;  // + barriers + alignment slack
   static int total(int a_stage_bytes, int a_stages, int b_stages, int stg_bufs, int res_bufs) {
@@ -120,17 +133,22 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 // tmIn : 2-D (C, positions) view of the padded input, box {64, 128 + 2W + 4}
 // tmW  : 3-D (cin, cout, 9 taps) packed weights, box {64, N_TILE, 3}
 // tmOut/tmRes : 2-D (C, positions) views of the padded output / residual, box {64, 128}
-constexpr int kHaloThreads = 384;  // 4 control warps + 8 epilogue warps (two per scheduler)
+constexpr int kHaloThreads = 384;  // EW = 8: 4 control warps + 8 epilogue warps (two per scheduler)
+constexpr int halo_threads(int ew) { return 128 + 32 * ew; }
 
-template <int N_TILE, bool BF16>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+template <int N_TILE, bool BF16, int EW = 8>
+__global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                     const HaloParams p) {
-  using S = HaloSmem<N_TILE>;
+  using S = HaloSmem<N_TILE, EW>;
+  static_assert(EW == 8 || EW == 4, "8 epilogue warps (one CTA per SM) or 4 (two CTAs per SM)");
+  static_assert(!(EW == 4 && N_TILE == 256), "the two-CTA-per-SM shape has 256 TMEM columns");
+  constexpr bool kSmall = S::kSmall;
+  constexpr int kEpiThreads = 32 * EW;
   const int kAStages = p.a_stages, kBStages = p.b_stages;
   constexpr int kAcc = S::kAccStages;
-  constexpr int kTmemCols = kAcc * N_TILE;
+  constexpr int kTmemCols = S::kTmemCols;
   constexpr int kChunksOut = N_TILE / 64;
 
   extern __shared__ uint8_t smem_raw[];
@@ -213,11 +231,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     if (p.flags & CONV_RESIDUAL) tma_prefetch_desc(&tmRes);
     for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], EW);  // one arrive per epilogue warp
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&res_full[i], 1);
-      mbar_init(&res_empty[i], 8);
+      mbar_init(&res_empty[i], EW);
     }
     fence_barrier_init();
   }
@@ -432,7 +450,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     }
   } else if (warp == 3) {
     // ===================== residual prefetcher: one 128 x 64 tile per output chunk, two buffers =====================
-    if (p.flags & CONV_RESIDUAL) {
+    if (!kSmall && (p.flags & CONV_RESIDUAL)) {
       int rb = 0;
       uint32_t rph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -453,9 +471,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: 8 warps; thread = one padded output position x 32 of the 64 channels ==========
+    // ===================== epilogue: EW warps; thread = one padded output position x 32 channels at a time ==========
+    // EW = 8: warp (ew, half) owns 32 of the 64 channels of every chunk; EW = 4: warp ew walks both halves.
     const int ew = (warp - 4) & 3;          // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const int half = (warp - 4) >> 2;       // which 32 columns of each 64-column chunk
+    const int half0 = kSmall ? 0 : (warp - 4) >> 2;
+    constexpr int kHalves = kSmall ? 2 : 1;
     const int row = ew * 32 + lane;
     const int etid = threadIdx.x - 128;
     const bool has_res = (p.flags & CONV_RESIDUAL) != 0;
@@ -488,7 +508,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       }
       // published before the first chunk barrier of this tile; two tables because a fast thread may enter the next
       // tile while others still copy this one out
-      if (p.out_planar && half == 0) row_dst[(ecount & 1) * 128 + row] = planar_row;
+      if (p.out_planar && half0 == 0) row_dst[(ecount & 1) * 128 + row] = planar_row;
+      // EW = 4: the residual comes straight from global memory (it was written two kernels ago and sits in L2); the
+      // 64 bytes of the NEXT (chunk, half) are fetched one step ahead so that their latency hides under this step's math
+      const uint16_t* res_g = nullptr;
+      uint4 rn[4] = {};
+      if constexpr (kSmall) {
+        if (has_res) {
+          res_g = p.res_ptr + static_cast<size_t>(q) * p.cout + c0;
+          const uint4* g4 = reinterpret_cast<const uint4*>(res_g);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) rn[qq] = __ldg(g4 + qq);
+        }
+      }
       if (etid == 0) DSK_TRACE(2, ecount * 8 + 0);
       if (p.late_trigger && tile + static_cast<int>(gridDim.x) >= num_tiles) pdl_launch_dependents();
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -501,54 +533,71 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           if (p.stg_bufs == 2) tma_store_wait_read<1>();
           else tma_store_wait_read<0>();
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, kEpiThreads);
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 2);
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64 + half * 32, v);
-        tmem_ld_wait();
-        if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 3);
-        if (has_res) mbar_wait(&res_full[rb], rph);
-        if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 4);
-        const uint8_t* res_row = smem_res + rb * kATileBytes + row * 128;
-        const int cbase = c0 + j * 64 + half * 32;
         uint8_t* my_row = stg + row * 128;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          float f[8];
-          // per-channel scale / bias from the parameter (constant) bank: the index is warp-uniform
-          float scv[8], biv[8];
+        for (int hx = 0; hx < kHalves; ++hx) {
+          const int half = kSmall ? hx : half0;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64 + half * 32, v);
+          uint4 rc[4] = {rn[0], rn[1], rn[2], rn[3]};
+          if constexpr (kSmall) {
+            const int nxt = (j * 2 + hx + 1);  // next (chunk, half) of this tile, if any
+            if (has_res && nxt < 2 * kChunksOut) {
+              const uint4* g4 = reinterpret_cast<const uint4*>(res_g + (nxt >> 1) * 64 + (nxt & 1) * 32);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            scv[e] = p.scale_c[cbase + qq * 8 + e];
-            biv[e] = p.bias_c[cbase + qq * 8 + e];
+              for (int qq = 0; qq < 4; ++qq) rn[qq] = __ldg(g4 + qq);
+            }
           }
+          tmem_ld_wait();
+          if (etid == 0 && j == 0 && hx == 0) DSK_TRACE(2, ecount * 8 + 3);
+          if constexpr (!kSmall) {
+            if (has_res) mbar_wait(&res_full[rb], rph);
+          }
+          if (etid == 0 && j == 0 && hx == 0) DSK_TRACE(2, ecount * 8 + 4);
+          const uint8_t* res_row = smem_res + rb * kATileBytes + row * 128;
+          const int cbase = c0 + j * 64 + half * 32;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[qq * 8 + e]), scv[e], biv[e]);
-          const int chunk16 = ((half * 4 + qq) ^ (row & 7)) << 4;  // 16-byte slot inside the swizzled 128-byte row
-          uint4* slot = reinterpret_cast<uint4*>(my_row + chunk16);
-          if (has_res) {
-            const uint4 r4 = *reinterpret_cast<const uint4*>(res_row + chunk16);
-            float2 t;
-            t = unpack2<BF16>(r4.x); f[0] += t.x; f[1] += t.y;
-            t = unpack2<BF16>(r4.y); f[2] += t.x; f[3] += t.y;
-            t = unpack2<BF16>(r4.z); f[4] += t.x; f[5] += t.y;
-            t = unpack2<BF16>(r4.w); f[6] += t.x; f[7] += t.y;
-          }
-          if (do_clip) {
+          for (int qq = 0; qq < 4; ++qq) {
+            float f[8];
+            // per-channel scale / bias from the parameter (constant) bank: the index is warp-uniform
+            float scv[8], biv[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], 0.0f), p.clip_hi);
+            for (int e = 0; e < 8; ++e) {
+              scv[e] = p.scale_c[cbase + qq * 8 + e];
+              biv[e] = p.bias_c[cbase + qq * 8 + e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[qq * 8 + e]), scv[e], biv[e]);
+            const int chunk16 = ((half * 4 + qq) ^ (row & 7)) << 4;  // 16-byte slot inside the swizzled 128-byte row
+            uint4* slot = reinterpret_cast<uint4*>(my_row + chunk16);
+            if (has_res) {
+              uint4 r4;
+              if constexpr (kSmall) r4 = rc[qq];
+              else r4 = *reinterpret_cast<const uint4*>(res_row + chunk16);
+              float2 t;
+              t = unpack2<BF16>(r4.x); f[0] += t.x; f[1] += t.y;
+              t = unpack2<BF16>(r4.y); f[2] += t.x; f[3] += t.y;
+              t = unpack2<BF16>(r4.z); f[4] += t.x; f[5] += t.y;
+              t = unpack2<BF16>(r4.w); f[6] += t.x; f[7] += t.y;
+            }
+            if (do_clip) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], 0.0f), p.clip_hi);
+            }
+            uint4 o;
+            o.x = pack2<BF16>(f[0], f[1]);
+            o.y = pack2<BF16>(f[2], f[3]);
+            o.z = pack2<BF16>(f[4], f[5]);
+            o.w = pack2<BF16>(f[6], f[7]);
+            if (junk) o = make_uint4(0u, 0u, 0u, 0u);  // pad positions stay zero
+            *slot = o;
           }
-          uint4 o;
-          o.x = pack2<BF16>(f[0], f[1]);
-          o.y = pack2<BF16>(f[2], f[3]);
-          o.z = pack2<BF16>(f[4], f[5]);
-          o.w = pack2<BF16>(f[6], f[7]);
-          if (junk) o = make_uint4(0u, 0u, 0u, 0u);  // pad positions stay zero
-          *slot = o;
         }
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 5);
         fence_proxy_async_smem();
-        if (has_res) {  // residual buffer consumed: hand it back to the prefetcher
+        if (!kSmall && has_res) {  // residual buffer consumed: hand it back to the prefetcher
           __syncwarp();
           if (lane == 0) mbar_arrive(&res_empty[rb]);
           if (++rb == p.res_bufs) {
@@ -556,7 +605,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
             rph ^= 1;
           }
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, kEpiThreads);
         if (!p.out_planar) {
           if (etid == 0) {
             tma_store_2d(&tmOut, stg, c0 + j * 64, q0);
@@ -564,11 +613,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           }
         } else {
           // parity-planar destination: rows scatter over four planes, so no TMA box; 8 lanes copy one 128-byte row
-          // (full lines per warp store), 4 rows per thread
+          // (full lines per warp store), 128 / (threads / 8) rows per thread
           const int chunk = etid & 7;
+          constexpr int kRowsPerPass = kEpiThreads / 8;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = i * 32 + (etid >> 3);
+          for (int i = 0; i < 128 / kRowsPerPass; ++i) {
+            const int rr = i * kRowsPerPass + (etid >> 3);
             uint16_t* d = row_dst[(ecount & 1) * 128 + rr];
             if (d != nullptr)
               *reinterpret_cast<uint4*>(d + j * 64 + chunk * 8) =

@@ -152,6 +152,7 @@ struct HaloLaunch {
   CUtensorMap tmIn, tmW, tmOut, tmRes;
   dsk::HaloParams p;
   int n_tile = 0;
+  int ew = 8;   // epilogue warps: 8 = one CTA per SM, 4 = the two-CTAs-per-SM shape (conv3x3_halo.cuh)
   int grid = 0;
   int smem = 0;
 };
@@ -239,6 +240,7 @@ struct dsk_handle_s {
   float* ones = nullptr;   // [512] = 1
   float* zeros = nullptr;  // [512] = 0
   float loss_scale = 0.f;  // 0 = automatic
+  bool defer_stats = false;  // dsk_set_defer_running_stats: train forwards record batch statistics, the caller commits them in order
   std::vector<dsk_train_ctx_s*> ctx_pool;
   // cached all-pairs plan (buffers + Gram GEMM descriptors) for the last (N, D)
   int ap_N = 0, ap_D = 0;
@@ -249,6 +251,7 @@ struct dsk_handle_s {
   bool use_graph = true;       // DSK_GRAPH=0: always launch the forward kernel by kernel
   bool conv1_pdl = true;       // debug knob DSK_CONV1_PDL=0: launch conv1 with plain stream serialisation
   bool late_trigger = false;   // debug knob DSK_LATE_TRIGGER=1: halo kernels release their dependents at the last tile
+  bool small_cta = false;      // DSK_SMALL_CTA=1: 128-channel-tile halo convs as two 256-thread CTAs per SM (measured slower: 1-tap weight boxes are TMA-request bound)
   bool planar_s2 = true;       // eval forward: run the 5x5 s2 convs in the halo kernel's parity-planar form (DSK_PLANAR_S2=0: generic kernel)
   long long* trace = nullptr;  // debug: device buffer [3][512] for conv3x3_halo_kernel clock stamps
   // optional per-launch timing (dsk_set_profiling): events recorded around every kernel of a forward
@@ -270,6 +273,8 @@ struct dsk_train_ctx_s {
   void* y[DSK_NUM_CONV] = {};          // after BN (+res) + clip (16-bit NHWC)
   float* mean[DSK_NUM_CONV] = {};
   float* rstd[DSK_NUM_CONV] = {};
+  float* unb[DSK_NUM_CONV] = {};       // unbiased batch variance (what the running_var update consumes)
+  bool stats_pending = false;          // forward ran with deferred running statistics: dsk_train_ctx_commit_stats owes the update
   float *pooled = nullptr, *fc_out = nullptr, *fc_part = nullptr, *inv_norm = nullptr;
   float *scale_t = nullptr, *shift_t = nullptr, *partial = nullptr, *coef = nullptr;
   float *g_fc = nullptr, *dP = nullptr, *dwacc = nullptr, *c1part = nullptr;
@@ -662,8 +667,11 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   // but halve the tile count: used when the layer still has enough tiles to spread over the SMs
   const int tiles_m_ = static_cast<int>((q_end - p.q_begin + 127) / 128);
   const int n_tile = cout == 64 ? 64 : (h->n256 && cout % 256 == 0 && tiles_m_ * (cout / 256) >= h->n256_min_tiles) ? 256 : 128;
-  const int tpb = n_tile == 256 ? 1 : 3;
+  // 128-channel tiles (stages 2-4: one or two tiles per SM and layer) run as two 256-thread CTAs per SM
+  const bool small = h->small_cta && n_tile == 128;
+  const int tpb = (n_tile == 256 || small) ? 1 : 3;
   L->n_tile = n_tile;
+  L->ew = small ? 4 : 8;
   p.tiles_c = cout / n_tile;
   p.chunks = cin / 64;
   p.cout = cout;
@@ -723,6 +731,7 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   p.plain3x3 = ksize == 3 ? 1 : 2;
   if (getenv("DSK_HALO_TABLE_ISSUE")) p.plain3x3 = 0;  // debug: table-driven MMA issue
   p.b_resident = (p.chunks == 1 && p.tiles_c == 1 && p.nboxes <= 3 && n_tile == 64) ? 1 : 0;
+  p.res_ptr = (flags & dsk::CONV_RESIDUAL) ? static_cast<const uint16_t*>(res) : nullptr;
   p.out_planar = out_planar;
   if (out_planar) {
     p.out_ptr = static_cast<uint16_t*>(out);
@@ -737,6 +746,18 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
     const bool has_res = (flags & dsk::CONV_RESIDUAL) != 0;
     const int b_bytes = tpb * n_tile * 128;
     const int fixed = dsk::HaloSmem<128>::kFixedBytes;  // the same for every tile width
+    if (small) {
+      // two CTAs per SM: (232448 B of shared memory per SM) / 2 minus the 1 KB the driver reserves per CTA
+      const int limit = 232448 / 2 - 1024;
+      p.a_stages = 2;
+      p.stg_bufs = 1;
+      p.res_bufs = 0;   // the residual is read from global memory (HaloParams::res_ptr)
+      int nb = (limit - fixed - p.a_stages * p.a_stage_bytes - p.stg_bufs * 16384) / b_bytes;
+      if (nb > dsk::kHaloMaxStages) nb = dsk::kHaloMaxStages;
+      if (nb < 2) return fail(DSK_ERR_INVALID, "halo conv (two CTAs per SM): shared memory does not fit");
+      p.b_stages = nb;
+      L->smem = p.a_stages * p.a_stage_bytes + p.b_stages * b_bytes + p.stg_bufs * 16384 + fixed;
+    } else {
     const int limit = 227 * 1024;
     p.a_stages = n_tile == 64 ? 3 : 2;
     p.stg_bufs = 2;
@@ -753,9 +774,11 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
     if (p.b_resident) p.b_stages = 3;
     if (p.b_stages < 2) return fail(DSK_ERR_INVALID, "halo conv: shared memory does not fit");
     L->smem = p.a_stages * p.a_stage_bytes + p.b_stages * b_bytes + (p.stg_bufs + p.res_bufs) * 16384 + fixed;
+    }
   }
   const int num_tiles = p.tiles_m * p.tiles_c;
-  L->grid = num_tiles < h->num_sms ? num_tiles : h->num_sms;
+  const int slots = h->num_sms * (small ? 2 : 1);
+  L->grid = num_tiles < slots ? num_tiles : slots;
   const uint64_t in_pos = static_cast<uint64_t>(npos) * (ksize == 5 ? 4 : 1);
   uint64_t idims[2] = {(uint64_t)cin, in_pos};
   uint64_t istr[1] = {2ull * cin};
@@ -778,15 +801,19 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   return make_tmap(&L->tmOut, bf, out_planar ? res_ptr : out, 2, odims, ostr, box_out);
 }
 
-template <int N_TILE, bool BF16>
+template <int N_TILE, bool BF16, int EW = 8>
 int launch_halo_t(const HaloLaunch& L, cudaStream_t s) {
-  auto kern = dsk::conv3x3_halo_kernel<N_TILE, BF16>;
-  if (int rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), 227 * 1024)) return rc;
-  CUDA_TRY(launch_pdl(kern, dim3(L.grid), dim3(dsk::kHaloThreads), L.smem, s, L.tmIn, L.tmW, L.tmOut, L.tmRes, L.p));
+  auto kern = dsk::conv3x3_halo_kernel<N_TILE, BF16, EW>;
+  if (int rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), EW == 4 ? 232448 / 2 - 1024 : 227 * 1024)) return rc;
+  CUDA_TRY(launch_pdl(kern, dim3(L.grid), dim3(dsk::halo_threads(EW)), L.smem, s, L.tmIn, L.tmW, L.tmOut, L.tmRes, L.p));
   return DSK_OK;
 }
 
 int launch_halo(const dsk_handle_s* h, const HaloLaunch& L, cudaStream_t s) {
+  if (L.ew == 4) {
+    if (L.n_tile != 128) return fail(DSK_ERR_INVALID, "two-CTAs-per-SM halo conv: 128-channel tiles only");
+    return h->bf16 ? launch_halo_t<128, true, 4>(L, s) : launch_halo_t<128, false, 4>(L, s);
+  }
   if (h->bf16)
     return L.n_tile == 64 ? launch_halo_t<64, true>(L, s) : L.n_tile == 128 ? launch_halo_t<128, true>(L, s) : launch_halo_t<256, true>(L, s);
   return L.n_tile == 64 ? launch_halo_t<64, false>(L, s) : L.n_tile == 128 ? launch_halo_t<128, false>(L, s) : launch_halo_t<256, false>(L, s);
@@ -931,6 +958,8 @@ int32_t dsk_create(dsk_handle* out, int32_t device, int32_t operand) {
   {
     const char* e = getenv("DSK_PLANAR_S2");  // default on; DSK_PLANAR_S2=0 runs the 5x5 s2 convs in the generic tap kernel
     h->planar_s2 = !(e && e[0] == '0');
+    e = getenv("DSK_SMALL_CTA");
+    if (e) h->small_cta = atoi(e) != 0;
     e = getenv("DSK_N256");
     h->n256 = e && e[0] == '1';
     e = getenv("DSK_N256_MIN_TILES");
@@ -1334,7 +1363,7 @@ static int ctx_create(dsk_handle h, int cap, int T, cudaStream_t s, dsk_train_ct
     bytes += (n + 1023) / 1024 * 1024;
     return o;
   };
-  size_t o_raw[DSK_NUM_CONV], o_y[DSK_NUM_CONV], o_mean[DSK_NUM_CONV], o_rstd[DSK_NUM_CONV];
+  size_t o_raw[DSK_NUM_CONV], o_y[DSK_NUM_CONV], o_mean[DSK_NUM_CONV], o_rstd[DSK_NUM_CONV], o_unb[DSK_NUM_CONV];
   size_t max_act = 0;
   for (int i = 0; i < DSK_NUM_CONV; ++i) {
     int H, W, C;
@@ -1345,6 +1374,7 @@ static int ctx_create(dsk_handle h, int cap, int T, cudaStream_t s, dsk_train_ct
     o_y[i] = take(act);
     o_mean[i] = take(C * 4);
     o_rstd[i] = take(C * 4);
+    o_unb[i] = take(C * 4);
   }
   const size_t o_pooled = take(static_cast<size_t>(B) * 2048 * 4), o_fc = take(static_cast<size_t>(B) * h->emb * 4);
   const size_t o_fc_part = take(static_cast<size_t>(dsk::kFcSplit) * B * h->emb * 4);
@@ -1373,6 +1403,7 @@ static int ctx_create(dsk_handle h, int cap, int T, cudaStream_t s, dsk_train_ct
     c->y[i] = b + o_y[i];
     c->mean[i] = reinterpret_cast<float*>(b + o_mean[i]);
     c->rstd[i] = reinterpret_cast<float*>(b + o_rstd[i]);
+    c->unb[i] = reinterpret_cast<float*>(b + o_unb[i]);
   }
   c->pooled = reinterpret_cast<float*>(b + o_pooled);
   c->fc_out = reinterpret_cast<float*>(b + o_fc);
@@ -1505,7 +1536,8 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
     KERNEL_CHECK();
     dsk::bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], h->w.bn_beta[i],
                                                            h->w.bn_running_mean[i], h->w.bn_running_var[i], 0.1f, 1e-5f,
-                                                           c->mean[i], c->rstd[i], c->scale_t, c->shift_t);
+                                                           c->mean[i], c->rstd[i], c->scale_t, c->shift_t, c->unb[i],
+                                                           h->defer_stats ? 0 : 1);
     KERNEL_CHECK();
     const uint16_t* res = (i % 3 == 2) ? (const uint16_t*)c->y[i - 2] : nullptr;
     dim3 ga(static_cast<unsigned>((M + 63) / 64), C / 64);
@@ -1532,7 +1564,36 @@ int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_
     KERNEL_CHECK();
   }
   c->forward_done = true;
+  c->stats_pending = h->defer_stats;
   *ctx_out = c;
+  return DSK_OK;
+}
+
+int32_t dsk_set_defer_running_stats(dsk_handle h, int32_t on) {
+  if (!h) return fail(DSK_ERR_INVALID, "null handle");
+  h->defer_stats = on != 0;
+  return DSK_OK;
+}
+
+int32_t dsk_train_ctx_commit_stats(dsk_handle h, dsk_train_ctx c, void* stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!c || !c->forward_done) return fail(DSK_ERR_STATE, "dsk_train_ctx_commit_stats: context has no pending forward");
+  if (!c->stats_pending) return DSK_OK;  // that forward already updated the running statistics itself
+  dsk::BnCommitParams p;
+  for (int i = 0; i < DSK_NUM_CONV; ++i) {
+    int H, W, C;
+    act_shape(i, c->T, H, W, C);
+    p.mean[i] = c->mean[i];
+    p.unbiased[i] = c->unb[i];
+    p.running_mean[i] = h->w.bn_running_mean[i];
+    p.running_var[i] = h->w.bn_running_var[i];
+    p.C[i] = C;
+  }
+  p.momentum = 0.1f;
+  dsk::bn_running_commit_kernel<<<dim3(4, DSK_NUM_CONV), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  KERNEL_CHECK();
+  c->stats_pending = false;
   return DSK_OK;
 }
 
@@ -1720,7 +1781,7 @@ int32_t dsk_bn_act_train_forward(dsk_handle h, const float* raw, const float* ga
   dsk::bn_stats_partial_kernel<<<dim3(gx, C / 64), 256, 0, s>>>(raw, M, C, partial);
   KERNEL_CHECK();
   dsk::bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(partial, gx, C, M, gamma, beta, running_mean, running_var, 0.1f,
-                                                         1e-5f, mean, rstd, sc, sh);
+                                                         1e-5f, mean, rstd, sc, sh, nullptr, 1);
   KERNEL_CHECK();
   dim3 ga(static_cast<unsigned>((M + 63) / 64), C / 64);
   if (h->bf16) dsk::bn_apply_kernel<true><<<ga, 256, 0, s>>>(raw, sc, sh, (const uint16_t*)res, (uint16_t*)y, M, C, 20.0f);

@@ -164,7 +164,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, 
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                   float* __restrict__ scale_out, float* __restrict__ shift_out) {
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                   float* __restrict__ unbiased_out, int update_running) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s, ss;
   if (!bn_partial_totals(partial, nblk, C, c, s, ss)) return;
@@ -178,8 +179,34 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, 
   scale_out[c] = sc;
   shift_out[c] = beta[c] - static_cast<float>(mean) * sc;
   const double unbiased = M > 1 ? var * static_cast<double>(M) / static_cast<double>(M - 1) : var;
-  running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
-  running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  if (unbiased_out) unbiased_out[c] = static_cast<float>(unbiased);
+  if (update_running) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// Deferred running-statistics update of ONE train-mode forward (all 12 BatchNorm layers in one launch): when several
+// forwards of a step run concurrently on different streams (DeepSpeakerModel.forward_triplet) their in-place
+// read-modify-writes of running_mean / running_var would race, so bn_finalize only records the batch mean and unbiased
+// variance and this kernel applies the momentum update afterwards, one forward after the other, in the order the
+// reference's sequential calls would have (train_triplet.py:215: a, p, n) - same operations, same bits.
+struct BnCommitParams {
+  const float* mean[12];
+  const float* unbiased[12];
+  float* running_mean[12];
+  float* running_var[12];
+  int C[12];
+  float momentum;
+};
+__global__ void bn_running_commit_kernel(const BnCommitParams p) {
+  const int layer = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C[layer]) return;
+  float* rm = p.running_mean[layer];
+  float* rv = p.running_var[layer];
+  rm[c] = (1.f - p.momentum) * rm[c] + p.momentum * p.mean[layer][c];
+  rv[c] = (1.f - p.momentum) * rv[c] + p.momentum * p.unbiased[layer][c];
 }
 
 // ---- forward: y = clip(raw*scale + shift (+res), 0, hi), NHWC 16-bit ---------------------------------------------

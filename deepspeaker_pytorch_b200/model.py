@@ -133,6 +133,29 @@ class DeepSpeakerModel(nn.Module):
         self.features = eng.forward(x, self.training)
         return self.features
 
+    def forward_triplet(self, anchor, positive, negative):
+        """The three forwards of a triplet step, ``model(data_a), model(data_p), model(data_n)``
+        (/root/reference/train_triplet.py:215), issued together: same three results (bit-identical embeddings, batch
+        statistics per call, running statistics updated in the order a, p, n), but in train mode the calls run on three
+        streams and overlap - as do their backwards.  In eval mode it is simply three forwards.  ``self.features`` is
+        left at the negative's embeddings, as after the reference's third call."""
+        xs = (anchor, positive, negative)
+        for x in xs:
+            if not x.is_cuda:
+                raise RuntimeError("DeepSpeakerModel (B200 engine) needs CUDA tensors; there is no CPU fallback")
+            if x.dim() != 4 or x.size(1) != 1 or x.size(3) != 64:
+                raise RuntimeError(f"expected input (B,1,T,64), got {tuple(x.shape)}")
+        if not self.training:
+            outs = [self.forward(x) for x in xs]
+        else:
+            from . import train as _train
+
+            eng = self._get_engine(anchor.device)
+            with torch.cuda.device(anchor.device):
+                outs = _train.forward_train_many(eng, list(xs))
+        self.features = outs[-1]
+        return tuple(outs)
+
     def forward_classifier(self, x):
         """model.py:220-223: embeddings -> ``model.classifier`` logits (B, num_classes), on the repo's fp32 GEMM
         kernels (``dsk_linear_forward/backward``); ``model.classifier`` only holds the parameters."""

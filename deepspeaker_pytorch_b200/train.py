@@ -75,21 +75,68 @@ class TrainForwardFn(torch.autograd.Function):
         return (None, None) + tuple(grads)
 
 
+def _forward_one(engine, x, params, need_grad):
+    """One train-mode forward on the CURRENT stream.  Returns (emb, library context or None if already released)."""
+    if need_grad:
+        emb = TrainForwardFn.apply(x, engine, *params)
+        return emb, emb.grad_fn.guard.tctx
+    B, _, T, _ = x.shape
+    emb = torch.empty(B, engine.module_ref.embedding_size, device=x.device, dtype=torch.float32)
+    tctx = ctypes.c_void_p()
+    L.check(engine.lib.dsk_rescnn_forward_train(engine.handle, x.data_ptr(), B, T, emb.data_ptr(), ctypes.byref(tctx),
+                                                L.cur_stream()), "dsk_rescnn_forward_train")
+    return emb, tctx
+
+
 def forward_train(engine, x):
     module = engine.module_ref
     engine.sync_weights(eval_mode=False)
     engine.train_calls += 1  # running statistics are about to change: invalidates the eval-mode BN fold
     params = _train_params(module)
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-    if need_grad:
-        emb = TrainForwardFn.apply(x, engine, *params)
-    else:
-        B, _, T, _ = x.shape
-        emb = torch.empty(B, module.embedding_size, device=x.device, dtype=torch.float32)
-        tctx = ctypes.c_void_p()
-        L.check(engine.lib.dsk_rescnn_forward_train(engine.handle, x.data_ptr(), B, T, emb.data_ptr(), ctypes.byref(tctx),
-                                                    L.cur_stream()), "dsk_rescnn_forward_train")
+    emb, tctx = _forward_one(engine, x, params, need_grad)
+    if not need_grad:
         L.check(engine.lib.dsk_train_ctx_release(engine.handle, tctx), "dsk_train_ctx_release")
     # nn.BatchNorm2d bookkeeping in train mode
     torch._foreach_add_([bn.num_batches_tracked for _, bn in conv_bn_modules(module)], 1)
     return emb
+
+
+def forward_train_many(engine, xs):
+    """Several independent train-mode forwards of one step (the anchor / positive / negative calls of
+    train_triplet.py:215) IN FLIGHT TOGETHER: forward k runs on its own side stream, so the HBM-bound BatchNorm passes
+    of one call overlap the tensor-core convs of another, and - because autograd replays every node on the stream its
+    forward ran on - so do the three backwards.  Results are those of the sequential calls, bit for bit: batch
+    statistics are per call anyway, and the running-statistics updates are recorded per call and committed afterwards
+    in call order (``dsk_train_ctx_commit_stats``).  All side streams are joined before returning."""
+    module = engine.module_ref
+    engine.sync_weights(eval_mode=False)
+    engine.train_calls += 1
+    params = _train_params(module)
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    dev = engine.device
+    cur = torch.cuda.current_stream(dev)
+    while len(engine.side_streams) < len(xs):
+        engine.side_streams.append(torch.cuda.Stream(dev))
+    xs = [x.contiguous().float() for x in xs]
+    L.check(engine.lib.dsk_set_defer_running_stats(engine.handle, 1), "dsk_set_defer_running_stats")
+    outs, ctxs = [], []
+    try:
+        for x, st in zip(xs, engine.side_streams):
+            st.wait_stream(cur)                      # inputs (and the parameters) were produced on the caller's stream
+            with torch.cuda.stream(st):
+                emb, tctx = _forward_one(engine, x, params, need_grad)
+            x.record_stream(st)
+            outs.append(emb)
+            ctxs.append(tctx)
+    finally:
+        L.check(engine.lib.dsk_set_defer_running_stats(engine.handle, 0), "dsk_set_defer_running_stats")
+    for st, emb in zip(engine.side_streams, outs):
+        cur.wait_stream(st)
+        emb.record_stream(cur)
+    for tctx in ctxs:                                # momentum updates in call order, on the caller's stream
+        L.check(engine.lib.dsk_train_ctx_commit_stats(engine.handle, tctx, L.cur_stream()), "dsk_train_ctx_commit_stats")
+        if not need_grad:
+            L.check(engine.lib.dsk_train_ctx_release(engine.handle, tctx), "dsk_train_ctx_release")
+    torch._foreach_add_([bn.num_batches_tracked for _, bn in conv_bn_modules(module)], len(xs))
+    return outs

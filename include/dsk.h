@@ -105,6 +105,14 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
  * dsk_rescnn_backward; x must stay alive until then.  Contexts are pooled inside the handle. */
 int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, dsk_train_ctx* ctx,
                                  void* stream);
+/* Several train-mode forwards of one step in flight at once (DeepSpeakerModel.forward_triplet runs the anchor / positive /
+ * negative forwards of train_triplet.py:215 on three streams so that the HBM-bound BatchNorm passes of one overlap the
+ * tensor-core convs of another): with `on` != 0 a train forward only RECORDS its batch statistics in the context and
+ * leaves running_mean / running_var alone; dsk_train_ctx_commit_stats then applies that forward's momentum update
+ * (all 12 layers, one launch).  Committing the contexts in the order of the reference's sequential calls (a, p, n) on
+ * one stream gives bit-identical running statistics.  A context must be committed before its backward consumes it. */
+int32_t dsk_set_defer_running_stats(dsk_handle h, int32_t on);
+int32_t dsk_train_ctx_commit_stats(dsk_handle h, dsk_train_ctx ctx, void* stream);
 /* Backward of that forward (what loss.backward() triggers, train_triplet.py:223): grad_emb (B,E) fp32 ->
  * gradients of every conv / BN / fc parameter, written (not accumulated) into `grads`.  Consumes the context. */
 int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx ctx, const float* grad_emb, const dsk_grads* grads,

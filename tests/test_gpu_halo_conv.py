@@ -11,11 +11,23 @@ from deepspeaker_pytorch_b200 import _lib as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def hl(cuda_dev):
+@pytest.fixture(scope="module", params=["two_ctas_per_sm", "one_cta_per_sm"])
+def hl(cuda_dev, request):
+    """Both CTA shapes of the halo kernel (csrc/conv3x3_halo.cuh): the 256-thread shape that shares an SM (default for
+    128-channel tiles) and the 384-thread one-per-SM shape; the handle reads DSK_SMALL_CTA when it is created."""
+    import os
+
     lib = L.load()
     h = ctypes.c_void_p()
-    L.check(lib.dsk_create(ctypes.byref(h), 0, L.DSK_F16), "dsk_create")
+    old = os.environ.get("DSK_SMALL_CTA")
+    os.environ["DSK_SMALL_CTA"] = "1" if request.param == "two_ctas_per_sm" else "0"
+    try:
+        L.check(lib.dsk_create(ctypes.byref(h), 0, L.DSK_F16), "dsk_create")
+    finally:
+        if old is None:
+            os.environ.pop("DSK_SMALL_CTA", None)
+        else:
+            os.environ["DSK_SMALL_CTA"] = old
     yield lib, h
     lib.dsk_destroy(h)
 

@@ -100,9 +100,10 @@ def test_fused_adagrad_matches_cpu_golden(cuda_dev, golden_dir):
         opt.zero_grad()
         p.grad.copy_(torch.from_numpy(g["grads"][it]).to(cuda_dev))
         opt.step()
-    # torch's CPU (non-foreach) Adagrad rounds `p += -clr * g / std` in a different order than the foreach CUDA
-    # implementation the kernel mirrors bit for bit (previous test): a few ulp over the 6 steps
-    assert np.allclose(p.detach().cpu().numpy(), g["p_final"], rtol=2e-6, atol=1e-8)
+    # torch's CUDA foreach Adagrad (which the kernel mirrors bit for bit, previous test) fuses sum += g*g into one FMA
+    # where the CPU rounds the product first: a few ulp over the 6 steps, absolute where p_final cancels towards zero
+    pmax = float(np.abs(g["p0"]).max())
+    assert np.allclose(p.detach().cpu().numpy(), g["p_final"], rtol=2e-6, atol=2e-6 * pmax)
     assert np.allclose(opt.flat_sum[:p.numel()].cpu().numpy(), g["sum_final"].ravel(), rtol=1e-6, atol=0)
 
 

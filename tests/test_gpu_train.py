@@ -219,3 +219,73 @@ def test_branch_b_step_b16_matches_reference_golden(cuda_dev, golden_dir):
         assert abs(p.grad.double().norm().item() - ref_norm) <= 0.05 * ref_norm + 1e-9, (kname, p.grad.norm().item(), ref_norm)
         checked += 1
     assert checked == 40
+
+
+def test_forward_triplet_is_bit_identical_to_three_sequential_calls(cuda_dev):
+    """forward_triplet (three train forwards + their backwards in flight on three streams, running statistics committed in
+    call order) against model(a), model(p), model(n) called one after the other (train_triplet.py:215): same bits for the
+    embeddings, the running statistics, num_batches_tracked and every gradient."""
+    sd = O.make_state_dict(4, 16)
+    xs = [O.make_input(12, 64, s, 3.0).cuda() for s in (7, 8, 9)]
+    res = []
+    for fused in (False, True):
+        m = make_model(sd, "fp16", cuda_dev)
+        for rep in range(2):                         # twice: contexts are recycled, running stats keep moving
+            outs = m.forward_triplet(*xs) if fused else (m(xs[0]), m(xs[1]), m(xs[2]))
+            loss = dsk.TripletMarginLoss(0.1).forward(*outs)
+            m.zero_grad()
+            loss.backward()
+        torch.cuda.synchronize()
+        res.append(([o.detach().clone() for o in outs], {k: v.clone() for k, v in m.state_dict().items()},
+                    {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}, loss.detach().clone()))
+    (o0, s0, g0, l0), (o1, s1, g1, l1) = res
+    assert torch.equal(l0, l1)
+    for a, b in zip(o0, o1):
+        assert torch.equal(a, b)
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), k
+    assert len(g0) == 38
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
+    # without autograd (train-mode BN under no_grad) the contexts are committed and released
+    m = make_model(sd, "fp16", cuda_dev)
+    with torch.no_grad():
+        e = m.forward_triplet(*xs)
+    m2 = make_model(sd, "fp16", cuda_dev)
+    with torch.no_grad():
+        e2 = (m2(xs[0]), m2(xs[1]), m2(xs[2]))
+    for a, b in zip(e, e2):
+        assert torch.equal(a, b)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k]), k
+    m.eval()
+    with torch.no_grad():
+        ev = m.forward_triplet(*xs)
+        assert torch.equal(ev[1], m(xs[1]))
+
+
+def test_train_step_helper_runs_both_branches_like_the_oracle(cuda_dev, golden_dir):
+    """steps.train_step (train_triplet.py:208-299 restated with device-side selection) against the oracle's branch-B step
+    on the reference golden's configuration, then a branch-A step through the same helper."""
+    g = np.load(os.path.join(golden_dir, "branch_b_step_b16.npz"))
+    B, T, s0, s1, s2, scale, lseed, margin = g["cfg"]
+    sd = O.make_state_dict(0, 16)
+    m = make_model(sd, "fp16", cuda_dev)
+    opt = dsk.FusedAdagrad(m.parameters(), lr=1e-3, lr_decay=1e-4)
+    xa, xp, xn = (O.make_input(int(B), int(T), int(s), float(scale)).cuda() for s in (s0, s1, s2))
+    label_p, label_n = torch.from_numpy(g["label_p"]).cuda(), torch.from_numpy(g["label_n"]).cuda()
+    r = dsk.train_step(m, opt, xa, xp, xn, label_p, label_n, margin=float(margin), epoch=1, min_softmax_epoch=2)
+    assert r is not None and r["selected"] == len(r["hard"])
+    assert len(set(r["hard"].tolist()) ^ set(g["hard"].tolist())) <= 2          # margin = median of d_n - d_p
+    if set(r["hard"].tolist()) == set(g["hard"].tolist()):
+        assert abs(r["ce"].item() - float(g["ce"])) <= 1e-3 * float(g["ce"])
+        assert abs(r["triplet"].item() - float(g["triplet"])) <= 2e-3 * 10.0
+    assert opt.step_count == 1 and m.model.classifier.weight.grad is not None
+    # nothing selected -> None, no optimizer step (train_triplet.py:263-264)
+    r0 = dsk.train_step(m, opt, xa, xp, xn, label_p, label_n, margin=-1e9, epoch=1)
+    assert r0 is None and opt.step_count == 1
+    # branch A through the same helper
+    rA = dsk.train_step(m, opt, xa, xp, xn, label_p, label_n, margin=0.1, epoch=3, min_softmax_epoch=2)
+    assert rA["ce"] is None and rA["selected"] == int(B) and opt.step_count == 2 and torch.isfinite(rA["loss"])
+    with pytest.raises(RuntimeError):
+        dsk.train_step(m.eval(), opt, xa, xp, xn, label_p, label_n, margin=0.1, epoch=3)
