@@ -60,6 +60,17 @@ struct HaloParams {
   int late_trigger;       // release the dependent kernel when this CTA starts its last tile instead of at entry
   int b_resident;         // all weight boxes of a CTA's channel tile fit the B ring: load once
   unsigned pitch_magic, img_magic;  // floor(2^32/d)+1 for d = W+1 and H+1: q/d == __umulhi(q, magic) for q < 2^32/d
+  // stream-K: a layer of this network has 1.3-2.4 tiles per SM, so whole-tile scheduling leaves 20-36 % of
+  // the SM-time of stages 2-4 idle in the last wave.  With stream_k the K loop of the layer (tiles x chunks x weight
+  // boxes "units") is cut into gridDim.x EQUAL contiguous ranges: a CTA's range covers the tail of one tile, whole
+  // tiles, and the head of another.  The CTA that holds the HEAD of a tile (units 0..) owns its epilogue; the CTAs
+  // holding later parts (always the FIRST thing in their range) dump their fp32 accumulator to sk_partial[cta] and raise
+  // sk_flags[cta]; the owner adds those partials in fixed order before its usual epilogue (deterministic).
+  int stream_k;
+  int sk_q, sk_r;      // CTA i owns units [i*sk_q + min(i, sk_r), (i+1)*sk_q + min(i+1, sk_r)) of the num_tiles * units of the layer
+  float* sk_partial;   // [gridDim.x][N_TILE / 4][128 rows] float4: slab-major, the 128 rows of one 4-column group contiguous
+                       // (a warp's 32 rows read / write 512 contiguous bytes per instruction)
+  int* sk_flags;       // [gridDim.x], zero outside a launch
   const uint16_t* res_ptr;  // residual tensor (padded layout, cout channels per position): read straight from global / L2
                             // by the 4-epilogue-warp variant, which has no shared memory to spare for residual tiles
   long long* trace;       // debug: per-role clock64 stamps of CTA 0 (nullptr = off); [role 0..2][512]
@@ -136,7 +147,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 constexpr int kHaloThreads = 384;  // EW = 8: 4 control warps + 8 epilogue warps (two per scheduler)
 constexpr int halo_threads(int ew) { return 128 + 32 * ew; }
 
-template <int N_TILE, bool BF16, int EW = 8>
+// KIND: the compile-time tap plan the MMA issuer runs - 1 = 3x3 (HaloPlan<1>), 2 = parity-planar 5x5 s2 (HaloPlan<2>).
+// One plan per instantiation (and the resident-weights burst only where it can occur, 64-channel 3x3): the kernel is
+// sensitive to its code size - adding the stream-K paths to the SAME instantiation (+45 % instructions, none of them
+// executed) slowed every layer by 12-17 % (profiles/r02_stream_k.md), so each instantiation carries only what it runs.
+template <int N_TILE, bool BF16, int EW = 8, bool SK = false, int KIND = 1>
 __global__ void __launch_bounds__(128 + 32 * EW, EW == 4 ? 2 : 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -185,6 +200,33 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     q0 = p.q_begin + mt * kTileM;
   };
 
+  // Work iteration shared by all roles.  Without stream-K a segment is a whole tile (tile = blockIdx.x + k * gridDim.x,
+  // units [0, units)); with it, consecutive pieces of this CTA's unit range [u_lo, u_hi).
+  const int units = p.chunks * p.nboxes;
+  constexpr bool sk = SK;  // a separate instantiation: the whole-tile kernel carries none of the stream-K code
+  // (32-bit arithmetic throughout: the host enables stream-K only while num_tiles * units fits comfortably)
+  auto sk_lo = [&](int i) -> int { return i * p.sk_q + (i < p.sk_r ? i : p.sk_r); };
+  const int u_lo = sk ? sk_lo(static_cast<int>(blockIdx.x)) : 0;
+  const int u_hi = sk ? sk_lo(static_cast<int>(blockIdx.x) + 1) : 0;
+  auto seg_begin = [&]() -> int { return sk ? u_lo : static_cast<int>(blockIdx.x); };
+  auto next_seg = [&](int& cur, int& tile, int& ub, int& ue) -> bool {
+    if (sk) {
+      if (cur >= u_hi) return false;
+      tile = cur / units;
+      ub = cur - tile * units;
+      const int rem = u_hi - cur;
+      ue = (units - ub) <= rem ? units : ub + rem;
+      cur += ue - ub;
+    } else {
+      if (cur >= num_tiles) return false;
+      tile = cur;
+      ub = 0;
+      ue = units;
+      cur += gridDim.x;
+    }
+    return true;
+  };
+
   // The producer warp owns the operand barriers and starts the first loads before the CTA-wide setup barrier: weight
   // boxes at once (parameters), the first halo tile right after the dependency wait.  The TMEM allocation and the
   // scale/bias fetch (a global-memory round trip) then overlap the first operand fetch instead of preceding it.
@@ -204,26 +246,32 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       fence_barrier_init();
     }
     __syncwarp();
-    if (static_cast<int>(blockIdx.x) < num_tiles) {
-      int c0, q0;
-      decode(blockIdx.x, c0, q0);
-      const int total_b = p.nboxes * p.chunks;
-      pre_b = total_b < kBStages ? total_b : kBStages;
-      if (elect_one_sync()) {
-        for (int i = 0; i < pre_b; ++i) {
-          const int ch = i / p.nboxes, b = i - ch * p.nboxes;
-          mbar_arrive_expect_tx(&b_full[i], S::kBStageBytes);
-          tma_load_3d(smem_b + i * S::kBStageBytes, &tmW, &b_full[i], ch * 64, c0, p.box_wtap[b]);
+    {
+      int cur0 = seg_begin();
+      int tile0, ub0, ue0;
+      if (next_seg(cur0, tile0, ub0, ue0)) {
+        int c0, q0;
+        decode(tile0, c0, q0);
+        const int seg_b = ue0 - ub0;  // weight boxes of the first segment
+        pre_b = seg_b < kBStages ? seg_b : kBStages;
+        if (elect_one_sync()) {
+          for (int i = 0; i < pre_b; ++i) {
+            const int u = ub0 + i;
+            const int ch = u / p.nboxes, b = u - ch * p.nboxes;
+            mbar_arrive_expect_tx(&b_full[i], S::kBStageBytes);
+            tma_load_3d(smem_b + i * S::kBStageBytes, &tmW, &b_full[i], ch * 64, c0, p.box_wtap[b]);
+          }
         }
+        __syncwarp();
+        pdl_wait();  // activations of the previous kernel are read below
+        if (elect_one_sync()) {
+          const int ch = ub0 / p.nboxes, b = ub0 - ch * p.nboxes;
+          mbar_arrive_expect_tx(&a_full[0], halo_rows * 128);
+          tma_load_2d(smem_a, &tmIn, &a_full[0], ch * 64, p.box_plane[b] * p.plane_positions + q0 - (p.W + 2));
+          DSK_TRACE(0, 0);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      pdl_wait();  // activations of the previous kernel are read below
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&a_full[0], halo_rows * 128);
-        tma_load_2d(smem_a, &tmIn, &a_full[0], 0, p.box_plane[0] * p.plane_positions + q0 - (p.W + 2));
-        DSK_TRACE(0, 0);
-      }
-      __syncwarp();
     }
   }
   if (warp == 1 && lane == 0) {
@@ -258,12 +306,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     bool first = true;
     int tcount = 1;
     bool a_pre = true;  // the first halo tile was issued in the prologue
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int c0, q0;
-      decode(tile, c0, q0);
-      for (int ch = 0; ch < p.chunks; ++ch) {
-        for (int b = 0; b < p.nboxes; ++b) {
-          if (p.box_first[b]) {
+    if constexpr (SK) {
+      int cur = seg_begin();
+      int tile, ub, ue;
+      while (next_seg(cur, tile, ub, ue)) {
+        int c0, q0;
+        decode(tile, c0, q0);
+        for (int u = ub; u < ue; ++u) {
+          const int ch = u / p.nboxes, b = u - ch * p.nboxes;
+          if (p.box_first[b] || u == ub) {  // a plane's halo tile: at its first box, or where this segment enters the plane
             if (a_pre) {
               a_pre = false;
             } else {
@@ -299,8 +350,53 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
             }
           }
         }
+        first = false;
       }
-      first = false;
+    } else {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int c0, q0;
+        decode(tile, c0, q0);
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          for (int b = 0; b < p.nboxes; ++b) {
+            if (p.box_first[b]) {
+              if (a_pre) {
+                a_pre = false;
+              } else {
+                mbar_wait(&a_empty[as], aph ^ 1);
+                if (elect_one_sync()) {
+                  mbar_arrive_expect_tx(&a_full[as], halo_rows * 128);
+                  tma_load_2d(smem_a + as * p.a_stage_bytes, &tmIn, &a_full[as], ch * 64,
+                              p.box_plane[b] * p.plane_positions + q0 - (p.W + 2));
+                  DSK_TRACE(0, tcount);
+                  ++tcount;
+                }
+                __syncwarp();
+              }
+              if (++as == kAStages) {
+                as = 0;
+                aph ^= 1;
+              }
+            }
+            if (!p.b_resident || first) {
+              if (pre_b > 0) {
+                --pre_b;
+              } else {
+                mbar_wait(&b_empty[bs], bph ^ 1);
+                if (elect_one_sync()) {
+                  mbar_arrive_expect_tx(&b_full[bs], S::kBStageBytes);
+                  tma_load_3d(smem_b + bs * S::kBStageBytes, &tmW, &b_full[bs], ch * 64, c0, p.box_wtap[b]);
+                }
+                __syncwarp();
+              }
+              if (++bs == kBStages) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+        }
+        first = false;
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-converged loop, one elected lane issues) =====================
@@ -311,149 +407,175 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     uint32_t acc_phase = 0;
     bool first = true;
     int tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      if (lane == 0) DSK_TRACE(1, tcount * 4 + 0);
-      const uint32_t d_tmem = tmem_base + acc * N_TILE;
-      if (p.plain3x3 == 1 && p.b_resident) {
-        // 64-channel 3x3: all nine weight taps stay resident; one straight-line burst of 36 MMAs per tile.
-        // Straight-line issue matters: descriptors are base + compile-time offsets + i*pitch, nothing is read from the
-        // tables between MMAs (the tensor pipe's queue drains while a table-driven issuer computes its next operands).
-        mbar_wait(&a_full[as], aph);
+    if constexpr (SK) {
+      int cur = seg_begin();
+      int tile, ub, ue;
+      while (next_seg(cur, tile, ub, ue)) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) DSK_TRACE(1, tcount * 4 + 1);
-        if (first) {
-          for (int b = 0; b < 3; ++b) mbar_wait(&b_full[b], 0);
-          tc_fence_after();
-        }
-        if (elect_one_sync()) {
-          const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a + as * p.a_stage_bytes));
-          const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b));
-#pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            const uint64_t dab = da0 + static_cast<uint64_t>(b * pitch) * 8;
-#pragma unroll
-            for (int t = 0; t < 3; ++t)
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(d_tmem, dab + (t * 8 + 2 * k), db0 + ((b * 3 + t) * (N_TILE * 8) + 2 * k), idesc,
-                         (b > 0 || t > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&a_empty[as]);
-          umma_commit(&tmem_full[acc]);
-        }
-        __syncwarp();
-        if (++as == kAStages) {
-          as = 0;
-          aph ^= 1;
-        }
-      } else if (p.plain3x3) {
-        auto issue_chunks = [&](auto plan_tag) {
-          using Plan = decltype(plan_tag);
-          for (int ch = 0; ch < p.chunks; ++ch) {
-            uint64_t da0 = 0;
-#pragma unroll
-            for (int b = 0; b < Plan::kBoxes; ++b) {
-              if (Plan::first(b)) {
-                mbar_wait(&a_full[as], aph);
-                tc_fence_after();
-                if (lane == 0 && ch == 0 && b == 0) DSK_TRACE(1, tcount * 4 + 1);
-                da0 = umma_desc_sw128(smem_u32(smem_a + as * p.a_stage_bytes));
-              }
-              mbar_wait(&b_full[bs], bph);
-              tc_fence_after();
-              if (elect_one_sync()) {
-                const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b + bs * S::kBStageBytes));
-#pragma unroll
-                for (int t = 0; t < Plan::ntaps(b); ++t) {
-                  const uint64_t da = da0 + static_cast<uint64_t>(Plan::row_i(b, t) * pitch + Plan::col_j(b, t)) * 8;
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_f16(d_tmem, da + 2 * k, db0 + (t * (N_TILE * 8) + 2 * k), idesc,
-                             (b > 0 || t > 0 || k > 0) ? 1u : (ch > 0 ? 1u : 0u));
+        if (lane == 0) DSK_TRACE(1, tcount * 4 + 0);
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        {
+          auto issue_chunks = [&](auto plan_tag) {
+            using Plan = decltype(plan_tag);
+            // units [ub, ue) of this tile (the whole K loop unless stream-K cut the tile): unit u = box b of chunk ch
+            for (int ch = ub / Plan::kBoxes; ch * Plan::kBoxes < ue; ++ch) {
+              uint64_t da0 = 0;
+  #pragma unroll
+              for (int b = 0; b < Plan::kBoxes; ++b) {
+                const int u = ch * Plan::kBoxes + b;
+                if (u < ub || u >= ue) continue;  // warp-uniform
+                if (Plan::first(b) || u == ub) {
+                  mbar_wait(&a_full[as], aph);
+                  tc_fence_after();
+                  if (lane == 0 && u == ub) DSK_TRACE(1, tcount * 4 + 1);
+                  da0 = umma_desc_sw128(smem_u32(smem_a + as * p.a_stage_bytes));
                 }
-                umma_commit(&b_empty[bs]);
-                if (Plan::last(b)) umma_commit(&a_empty[as]);
-                if (b == Plan::kBoxes - 1 && ch == p.chunks - 1) umma_commit(&tmem_full[acc]);
-              }
-              __syncwarp();
-              if (++bs == kBStages) {
-                bs = 0;
-                bph ^= 1;
-              }
-              if (Plan::last(b)) {
-                if (++as == kAStages) {
-                  as = 0;
-                  aph ^= 1;
+                mbar_wait(&b_full[bs], bph);
+                tc_fence_after();
+                const bool rel_a = Plan::last(b) || u == ue - 1;
+                if (elect_one_sync()) {
+                  const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b + bs * S::kBStageBytes));
+  #pragma unroll
+                  for (int t = 0; t < Plan::ntaps(b); ++t) {
+                    const uint64_t da = da0 + static_cast<uint64_t>(Plan::row_i(b, t) * pitch + Plan::col_j(b, t)) * 8;
+  #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_f16(d_tmem, da + 2 * k, db0 + (t * (N_TILE * 8) + 2 * k), idesc,
+                               (t > 0 || k > 0) ? 1u : (u > ub ? 1u : 0u));
+                  }
+                  umma_commit(&b_empty[bs]);
+                  if (rel_a) umma_commit(&a_empty[as]);
+                  if (u == ue - 1) umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++bs == kBStages) {
+                  bs = 0;
+                  bph ^= 1;
+                }
+                if (rel_a) {
+                  if (++as == kAStages) {
+                    as = 0;
+                    aph ^= 1;
+                  }
                 }
               }
             }
-          }
-        };
-        if (p.plain3x3 == 1) issue_chunks(HaloPlan<1, S::kTapsPerBox>{});
-        else issue_chunks(HaloPlan<2, S::kTapsPerBox>{});
-      } else
-      for (int ch = 0; ch < p.chunks; ++ch) {
-        uint64_t da0 = 0;
-        for (int b = 0; b < p.nboxes; ++b) {
-          if (p.box_first[b]) {
-            mbar_wait(&a_full[as], aph);
-            tc_fence_after();
-            if (lane == 0 && ch == 0 && b == 0) DSK_TRACE(1, tcount * 4 + 1);
-            da0 = umma_desc_sw128(smem_u32(smem_a + as * p.a_stage_bytes));
-          }
-          // resident weights (one chunk, boxes <= ring size): box b sits in ring slot b for the whole kernel
-          const int slot = p.b_resident ? b : bs;
-          if (!p.b_resident || first) {
-            mbar_wait(&b_full[slot], bph);
+          };
+          issue_chunks(HaloPlan<KIND, S::kTapsPerBox>{});
+        }
+        if (lane == 0) DSK_TRACE(1, tcount * 4 + 2);
+        ++tcount;
+        if (++acc == kAcc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        first = false;
+      }
+    } else {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        if (lane == 0) DSK_TRACE(1, tcount * 4 + 0);
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        constexpr bool kResident = N_TILE == 64 && KIND == 1 && !kSmall;  // the only shape whose 9 taps fit the ring
+        bool resident = false;
+        if constexpr (kResident) resident = p.b_resident != 0;
+        if (resident) {
+          // 64-channel 3x3: all nine weight taps stay resident; one straight-line burst of 36 MMAs per tile.
+          // Straight-line issue matters: descriptors are base + compile-time offsets + i*pitch, nothing is read from the
+          // tables between MMAs (the tensor pipe's queue drains while a table-driven issuer computes its next operands).
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          if (lane == 0) DSK_TRACE(1, tcount * 4 + 1);
+          if (first) {
+            for (int b = 0; b < 3; ++b) mbar_wait(&b_full[b], 0);
             tc_fence_after();
           }
           if (elect_one_sync()) {
-            const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b + slot * S::kBStageBytes));
-            const int nt = p.box_ntaps[b];
-            for (int t = 0; t < nt; ++t) {
-              // tap t of the box: A rows shifted by tap_shift (x 128 B = +8 per row in the addr>>4 field); B tap t is
-              // N_TILE*128 B further; K16 step = +2
-              const uint64_t da = da0 + static_cast<uint64_t>(p.tap_shift[b][t]) * 8;
-              const uint64_t db = db0 + static_cast<uint64_t>(t * (N_TILE * 8));
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (ch > 0 || b > 0 || t > 0 || k > 0) ? 1u : 0u);
+            const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a + as * p.a_stage_bytes));
+            const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b));
+  #pragma unroll
+            for (int b = 0; b < 3; ++b) {
+              const uint64_t dab = da0 + static_cast<uint64_t>(b * pitch) * 8;
+  #pragma unroll
+              for (int t = 0; t < 3; ++t)
+  #pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(d_tmem, dab + (t * 8 + 2 * k), db0 + ((b * 3 + t) * (N_TILE * 8) + 2 * k), idesc,
+                           (b > 0 || t > 0 || k > 0) ? 1u : 0u);
             }
-            if (!p.b_resident) umma_commit(&b_empty[bs]);
-            if (p.box_last[b]) umma_commit(&a_empty[as]);
-            if (ch == p.chunks - 1 && b == p.nboxes - 1) umma_commit(&tmem_full[acc]);
+            umma_commit(&a_empty[as]);
+            umma_commit(&tmem_full[acc]);
           }
           __syncwarp();
-          if (!p.b_resident) {
-            if (++bs == kBStages) {
-              bs = 0;
-              bph ^= 1;
-            }
+          if (++as == kAStages) {
+            as = 0;
+            aph ^= 1;
           }
-          if (p.box_last[b]) {
-            if (++as == kAStages) {
-              as = 0;
-              aph ^= 1;
+        } else {
+          auto issue_chunks = [&](auto plan_tag) {
+            using Plan = decltype(plan_tag);
+            for (int ch = 0; ch < p.chunks; ++ch) {
+              uint64_t da0 = 0;
+  #pragma unroll
+              for (int b = 0; b < Plan::kBoxes; ++b) {
+                if (Plan::first(b)) {
+                  mbar_wait(&a_full[as], aph);
+                  tc_fence_after();
+                  if (lane == 0 && ch == 0 && b == 0) DSK_TRACE(1, tcount * 4 + 1);
+                  da0 = umma_desc_sw128(smem_u32(smem_a + as * p.a_stage_bytes));
+                }
+                mbar_wait(&b_full[bs], bph);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                  const uint64_t db0 = umma_desc_sw128(smem_u32(smem_b + bs * S::kBStageBytes));
+  #pragma unroll
+                  for (int t = 0; t < Plan::ntaps(b); ++t) {
+                    const uint64_t da = da0 + static_cast<uint64_t>(Plan::row_i(b, t) * pitch + Plan::col_j(b, t)) * 8;
+  #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_f16(d_tmem, da + 2 * k, db0 + (t * (N_TILE * 8) + 2 * k), idesc,
+                               (b > 0 || t > 0 || k > 0) ? 1u : (ch > 0 ? 1u : 0u));
+                  }
+                  umma_commit(&b_empty[bs]);
+                  if (Plan::last(b)) umma_commit(&a_empty[as]);
+                  if (b == Plan::kBoxes - 1 && ch == p.chunks - 1) umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++bs == kBStages) {
+                  bs = 0;
+                  bph ^= 1;
+                }
+                if (Plan::last(b)) {
+                  if (++as == kAStages) {
+                    as = 0;
+                    aph ^= 1;
+                  }
+                }
+              }
             }
-          }
+          };
+          issue_chunks(HaloPlan<KIND, S::kTapsPerBox>{});
         }
+        if (lane == 0) DSK_TRACE(1, tcount * 4 + 2);
+        ++tcount;
+        if (++acc == kAcc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        first = false;
       }
-      if (lane == 0) DSK_TRACE(1, tcount * 4 + 2);
-      ++tcount;
-      if (++acc == kAcc) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-      first = false;
     }
   } else if (warp == 3) {
     // ===================== residual prefetcher: one 128 x 64 tile per output chunk, two buffers =====================
     if (!kSmall && (p.flags & CONV_RESIDUAL)) {
       int rb = 0;
       uint32_t rph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int cur = seg_begin();
+      int tile, ub, ue;
+      while (next_seg(cur, tile, ub, ue)) {
+        if (ub > 0) continue;  // a later part of a tile: no epilogue here, its owner adds the residual
         int c0, q0;
         decode(tile, c0, q0);
         for (int j = 0; j < kChunksOut; ++j) {
@@ -487,9 +609,52 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     uint32_t rph = 0;
     int buf = 0;
     int ecount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int cur = seg_begin();
+    int tile, ub, ue;
+    while (next_seg(cur, tile, ub, ue)) {
       int c0, q0;
       decode(tile, c0, q0);
+      if (SK && ub > 0) {
+        // ---- stream-K: a later part of a tile.  Dump the raw fp32 accumulator for the tile's owner and raise this CTA's flag.
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        float4* dst = reinterpret_cast<float4*>(p.sk_partial) + static_cast<size_t>(blockIdx.x) * (N_TILE / 4) * kTileM + row;
+#pragma unroll 1
+        for (int j = 0; j < kChunksOut; ++j) {
+#pragma unroll
+          for (int hx = 0; hx < kHalves; ++hx) {
+            const int half = kSmall ? hx : half0;
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64 + half * 32, v);
+            tmem_ld_wait();
+            float4* d4 = dst + static_cast<size_t>(j * 16 + half * 8) * kTileM;   // 4-column group g of the tile at dst[g * 128]
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq)
+              d4[qq * kTileM] = make_float4(__uint_as_float(v[4 * qq]), __uint_as_float(v[4 * qq + 1]),
+                                            __uint_as_float(v[4 * qq + 2]), __uint_as_float(v[4 * qq + 3]));
+          }
+        }
+        __threadfence();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        named_bar_sync(1, kEpiThreads);  // every thread's partial rows are written and fenced
+        if (etid == 0) st_release_gpu(p.sk_flags + blockIdx.x, 1);
+        if (++acc == kAcc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
+      // stream-K: the head of a cut tile owns its epilogue; the parts live in the next CTAs' ranges (each CTA's range
+      // starts with at most one such part, so CTA blockIdx.x + c holds part c)
+      int n_parts = 0;
+      if (SK && ue < units) {
+        const int tile_end = (tile + 1) * units;
+        while (static_cast<int>(blockIdx.x) + 1 + n_parts < static_cast<int>(gridDim.x) &&
+               sk_lo(static_cast<int>(blockIdx.x) + 1 + n_parts) < tile_end)
+          ++n_parts;
+      }
       const int q = q0 + row;
       const int R = static_cast<int>(__umulhi(static_cast<unsigned>(q), p.pitch_magic));
       const int cc = q - R * pitch;
@@ -522,7 +687,26 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         }
       }
       if (etid == 0) DSK_TRACE(2, ecount * 8 + 0);
-      if (p.late_trigger && tile + static_cast<int>(gridDim.x) >= num_tiles) pdl_launch_dependents();
+      if (p.late_trigger && (sk ? cur >= u_hi : cur >= num_tiles)) pdl_launch_dependents();
+      // stream-K owner: the other parts of this tile were the FIRST work of their CTAs, so they are normally complete long
+      // before this CTA's own MMAs are: wait for their flags now and fetch the first slab of the first part, under the
+      // tail of the MMAs instead of after it
+      float4 pre[8];
+      if (SK && n_parts > 0) {
+        if (etid == 0) {
+          const long long t_wait = clock64();
+          for (int c = 1; c <= n_parts; ++c)
+            while (ld_acquire_gpu(p.sk_flags + blockIdx.x + c) == 0) {
+              // a part that never arrives is a scheduling bug: fail the launch instead of hanging the device (~2 s)
+              if (clock64() - t_wait > (1ll << 32)) __trap();
+            }
+        }
+        named_bar_sync(1, kEpiThreads);
+        const float4* s4 = reinterpret_cast<const float4*>(p.sk_partial) +
+                           (static_cast<size_t>(blockIdx.x + 1) * (N_TILE / 4) + (kSmall ? 0 : half0) * 8) * kTileM + row;
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) pre[qq] = __ldcg(s4 + qq * kTileM);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (etid == 0) DSK_TRACE(2, ecount * 8 + 1);
@@ -551,6 +735,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
             }
           }
           tmem_ld_wait();
+          if (SK && n_parts > 0) {  // fixed order: own head part + part 1 + part 2 ...
+            for (int c = 1; c <= n_parts; ++c) {
+              const float4* s4 = reinterpret_cast<const float4*>(p.sk_partial) +
+                                 (static_cast<size_t>(blockIdx.x + c) * (N_TILE / 4) + j * 16 + half * 8) * kTileM + row;
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) {
+                const float4 t4 = (c == 1 && j == 0 && hx == 0) ? pre[qq] : __ldcg(s4 + qq * kTileM);
+                v[4 * qq + 0] = __float_as_uint(__uint_as_float(v[4 * qq + 0]) + t4.x);
+                v[4 * qq + 1] = __float_as_uint(__uint_as_float(v[4 * qq + 1]) + t4.y);
+                v[4 * qq + 2] = __float_as_uint(__uint_as_float(v[4 * qq + 2]) + t4.z);
+                v[4 * qq + 3] = __float_as_uint(__uint_as_float(v[4 * qq + 3]) + t4.w);
+              }
+            }
+          }
           if (etid == 0 && j == 0 && hx == 0) DSK_TRACE(2, ecount * 8 + 3);
           if constexpr (!kSmall) {
             if (has_res) mbar_wait(&res_full[rb], rph);
@@ -628,6 +826,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 6);
         if (++buf == p.stg_bufs) buf = 0;
       }
+      if (SK && n_parts > 0 && etid == 0)  // every thread passed the last chunk's barrier after reading the partials
+        for (int c = 1; c <= n_parts; ++c) p.sk_flags[blockIdx.x + c] = 0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);

@@ -251,6 +251,9 @@ struct dsk_handle_s {
   bool use_graph = true;       // DSK_GRAPH=0: always launch the forward kernel by kernel
   bool conv1_pdl = true;       // debug knob DSK_CONV1_PDL=0: launch conv1 with plain stream serialisation
   bool late_trigger = false;   // debug knob DSK_LATE_TRIGGER=1: halo kernels release their dependents at the last tile
+  bool stream_k = false;       // DSK_STREAM_K=1: equal K ranges per CTA (conv3x3_halo.cuh); measured 10 % SLOWER than whole tiles (profiles/r02_stream_k.md)
+  float* sk_partial = nullptr; // stream-K partial accumulators [num_sms][128][256] fp32 and flags, one set per handle
+  int* sk_flags = nullptr;
   bool small_cta = false;      // DSK_SMALL_CTA=1: 128-channel-tile halo convs as two 256-thread CTAs per SM (measured slower: 1-tap weight boxes are TMA-request bound)
   bool planar_s2 = true;       // eval forward: run the 5x5 s2 convs in the halo kernel's parity-planar form (DSK_PLANAR_S2=0: generic kernel)
   long long* trace = nullptr;  // debug: device buffer [3][512] for conv3x3_halo_kernel clock stamps
@@ -729,7 +732,6 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   }
   // all weight boxes of a CTA fit the B ring and every tile of the CTA uses the same ones: load them once
   p.plain3x3 = ksize == 3 ? 1 : 2;
-  if (getenv("DSK_HALO_TABLE_ISSUE")) p.plain3x3 = 0;  // debug: table-driven MMA issue
   p.b_resident = (p.chunks == 1 && p.tiles_c == 1 && p.nboxes <= 3 && n_tile == 64) ? 1 : 0;
   p.res_ptr = (flags & dsk::CONV_RESIDUAL) ? static_cast<const uint16_t*>(res) : nullptr;
   p.out_planar = out_planar;
@@ -779,6 +781,35 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   const int num_tiles = p.tiles_m * p.tiles_c;
   const int slots = h->num_sms * (small ? 2 : 1);
   L->grid = num_tiles < slots ? num_tiles : slots;
+  // stream-K: equal unit ranges per CTA instead of whole tiles when that shortens the longest CTA by > 5 %
+  p.stream_k = 0;
+  if (h->stream_k && !small && !p.b_resident && p.plain3x3 && n_tile != 64) {
+    const long units = static_cast<long>(p.chunks) * p.nboxes;
+    const long total = units * num_tiles;
+    long g = total / 6;  // at least 6 weight boxes per CTA
+    if (g > h->num_sms) g = h->num_sms;
+    if (g < 1) g = 1;
+    const long span_tiles = (num_tiles + L->grid - 1) / L->grid * units;
+    const long span_sk = (total + g - 1) / g;
+    if (span_sk * 105 < span_tiles * 100 && total < (1l << 28)) {
+      if (!h->sk_partial) {
+        dsk_handle_s* hh = const_cast<dsk_handle_s*>(h);
+        const size_t nb = static_cast<size_t>(h->num_sms) * 128 * 256 * sizeof(float);
+        if (cudaMalloc(reinterpret_cast<void**>(&hh->sk_partial), nb) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&hh->sk_flags), h->num_sms * sizeof(int)) != cudaSuccess ||
+            cudaMemset(hh->sk_flags, 0, h->num_sms * sizeof(int)) != cudaSuccess) {
+          cudaGetLastError();
+          return fail(DSK_ERR_CUDA, "halo conv: stream-K workspace allocation failed");
+        }
+      }
+      p.stream_k = 1;
+      p.sk_q = static_cast<int>(total / g);
+      p.sk_r = static_cast<int>(total % g);
+      p.sk_partial = h->sk_partial;
+      p.sk_flags = h->sk_flags;
+      L->grid = static_cast<int>(g);
+    }
+  }
   const uint64_t in_pos = static_cast<uint64_t>(npos) * (ksize == 5 ? 4 : 1);
   uint64_t idims[2] = {(uint64_t)cin, in_pos};
   uint64_t istr[1] = {2ull * cin};
@@ -801,22 +832,35 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   return make_tmap(&L->tmOut, bf, out_planar ? res_ptr : out, 2, odims, ostr, box_out);
 }
 
-template <int N_TILE, bool BF16, int EW = 8>
+template <int N_TILE, bool BF16, int EW, bool SK, int KIND>
 int launch_halo_t(const HaloLaunch& L, cudaStream_t s) {
-  auto kern = dsk::conv3x3_halo_kernel<N_TILE, BF16, EW>;
+  auto kern = dsk::conv3x3_halo_kernel<N_TILE, BF16, EW, SK, KIND>;
   if (int rc = ensure_smem_optin(reinterpret_cast<const void*>(kern), EW == 4 ? 232448 / 2 - 1024 : 227 * 1024)) return rc;
   CUDA_TRY(launch_pdl(kern, dim3(L.grid), dim3(dsk::halo_threads(EW)), L.smem, s, L.tmIn, L.tmW, L.tmOut, L.tmRes, L.p));
   return DSK_OK;
 }
 
+// one instantiation per (tile width, operand type, CTA shape, scheduling, tap plan): each carries only the code it runs
+template <int N_TILE, int EW, bool SK>
+int launch_halo_v(const dsk_handle_s* h, const HaloLaunch& L, cudaStream_t s) {
+  const bool k5 = L.p.plain3x3 == 2;
+  if (h->bf16) return k5 ? launch_halo_t<N_TILE, true, EW, SK, 2>(L, s) : launch_halo_t<N_TILE, true, EW, SK, 1>(L, s);
+  return k5 ? launch_halo_t<N_TILE, false, EW, SK, 2>(L, s) : launch_halo_t<N_TILE, false, EW, SK, 1>(L, s);
+}
+
 int launch_halo(const dsk_handle_s* h, const HaloLaunch& L, cudaStream_t s) {
+  if (L.p.plain3x3 != 1 && L.p.plain3x3 != 2) return fail(DSK_ERR_INVALID, "halo conv: unknown tap plan %d", L.p.plain3x3);
   if (L.ew == 4) {
-    if (L.n_tile != 128) return fail(DSK_ERR_INVALID, "two-CTAs-per-SM halo conv: 128-channel tiles only");
-    return h->bf16 ? launch_halo_t<128, true, 4>(L, s) : launch_halo_t<128, false, 4>(L, s);
+    if (L.n_tile != 128 || L.p.stream_k) return fail(DSK_ERR_INVALID, "two-CTAs-per-SM halo conv: 128-channel whole tiles only");
+    return launch_halo_v<128, 4, false>(h, L, s);
   }
-  if (h->bf16)
-    return L.n_tile == 64 ? launch_halo_t<64, true>(L, s) : L.n_tile == 128 ? launch_halo_t<128, true>(L, s) : launch_halo_t<256, true>(L, s);
-  return L.n_tile == 64 ? launch_halo_t<64, false>(L, s) : L.n_tile == 128 ? launch_halo_t<128, false>(L, s) : launch_halo_t<256, false>(L, s);
+  if (L.p.stream_k) {
+    if (L.n_tile == 128) return launch_halo_v<128, 8, true>(h, L, s);
+    if (L.n_tile == 256) return launch_halo_v<256, 8, true>(h, L, s);
+    return fail(DSK_ERR_INVALID, "stream-K halo conv: 128- or 256-channel tiles only");
+  }
+  return L.n_tile == 64 ? launch_halo_v<64, 8, false>(h, L, s)
+                        : L.n_tile == 128 ? launch_halo_v<128, 8, false>(h, L, s) : launch_halo_v<256, 8, false>(h, L, s);
 }
 
 int check_handle(dsk_handle h) {
@@ -960,6 +1004,8 @@ int32_t dsk_create(dsk_handle* out, int32_t device, int32_t operand) {
     h->planar_s2 = !(e && e[0] == '0');
     e = getenv("DSK_SMALL_CTA");
     if (e) h->small_cta = atoi(e) != 0;
+    e = getenv("DSK_STREAM_K");
+    if (e) h->stream_k = atoi(e) != 0;
     e = getenv("DSK_N256");
     h->n256 = e && e[0] == '1';
     e = getenv("DSK_N256_MIN_TILES");
@@ -1002,6 +1048,8 @@ int32_t dsk_destroy(dsk_handle h) {
     cudaFree(h->fc_wq);
   }
   cudaFree(h->ws);
+  cudaFree(h->sk_partial);
+  cudaFree(h->sk_flags);
   cudaFree(h->ap_buf);
   cudaFree(h->ones);
   cudaFree(h->zeros);

@@ -158,6 +158,12 @@ __device__ __forceinline__ bool bn_partial_totals(const float* __restrict__ part
   return true;
 }
 
+// running = (1 - momentum) * running + momentum * batch, with the roundings pinned (one multiply, one FMA) so that the
+// in-kernel update of bn_finalize_kernel and the deferred bn_running_commit_kernel produce the same bits
+__device__ __forceinline__ float bn_momentum_update(float running, float batch, float momentum) {
+  return __fmaf_rn(momentum, batch, __fmul_rn(1.f - momentum, running));
+}
+
 // mean / biased var -> rstd, scale = gamma*rstd, shift = beta - mean*scale; running stats (momentum, unbiased var)
 // grid ceil(C/32), block 1024
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long M,
@@ -181,8 +187,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, 
   const double unbiased = M > 1 ? var * static_cast<double>(M) / static_cast<double>(M - 1) : var;
   if (unbiased_out) unbiased_out[c] = static_cast<float>(unbiased);
   if (update_running) {
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    running_mean[c] = bn_momentum_update(running_mean[c], static_cast<float>(mean), momentum);
+    running_var[c] = bn_momentum_update(running_var[c], static_cast<float>(unbiased), momentum);
   }
 }
 
@@ -205,8 +211,8 @@ __global__ void bn_running_commit_kernel(const BnCommitParams p) {
   if (c >= p.C[layer]) return;
   float* rm = p.running_mean[layer];
   float* rv = p.running_var[layer];
-  rm[c] = (1.f - p.momentum) * rm[c] + p.momentum * p.mean[layer][c];
-  rv[c] = (1.f - p.momentum) * rv[c] + p.momentum * p.unbiased[layer][c];
+  rm[c] = bn_momentum_update(rm[c], p.mean[layer][c], p.momentum);
+  rv[c] = bn_momentum_update(rv[c], p.unbiased[layer][c], p.momentum);
 }
 
 // ---- forward: y = clip(raw*scale + shift (+res), 0, hi), NHWC 16-bit ---------------------------------------------

@@ -67,9 +67,12 @@ def test_full_size_properties(models):
         assert torch.allclose(e1.norm(dim=1), torch.full((64,), 10.0, device=x.device), atol=1e-3)
         perm = torch.randperm(64, device=x.device)
         ep = m(x[perm].contiguous())
-        assert torch.allclose(ep, e1[perm], atol=2e-5)                # each utterance is independent of its batch
+        # each utterance is independent of its batch (eval BN).  Under stream-K scheduling the place where a tile's K loop
+        # is cut depends on the batch size and the tile index, so fp32 partial sums associate differently: a last-bit
+        # difference that the 16-bit activation storage occasionally turns into one fp16 ulp (<= 5e-5 of the norm)
+        assert torch.allclose(ep, e1[perm], atol=5e-4)
         e_small = m(x[5:8].contiguous())
-        assert torch.allclose(e_small, e1[5:8], atol=2e-5)
+        assert torch.allclose(e_small, e1[5:8], atol=5e-4)
         assert torch.isfinite(m(torch.full_like(x, 1e4))).all()       # clip at 20 keeps everything finite
 
 
@@ -153,7 +156,23 @@ def test_wide_tile_variant_is_bit_identical(models):
     """DSK_N256=1 runs the >=256-channel convs with 128x256 tiles and single-tap weight boxes: same K order per
     output element, so the embeddings must not change by a bit."""
     sd, ms = models
-    mw = _fresh_model(sd, {"DSK_N256": "1", "DSK_N256_MIN_TILES": "1"})
+    mw = _fresh_model(sd, {"DSK_N256": "1", "DSK_N256_MIN_TILES": "1", "DSK_STREAM_K": "0"})
+    mn = _fresh_model(sd, {"DSK_STREAM_K": "0"})      # whole-tile scheduling on both sides: stream-K cuts K per tile shape
     x = O.make_input(9, 64, seed=70, scale=5.0).cuda()
     with torch.no_grad():
-        assert torch.equal(mw(x), ms["fp16"](x))
+        assert torch.equal(mw(x), mn(x))
+
+
+def test_stream_k_matches_whole_tile_scheduling(models):
+    """Stream-K (equal K ranges per CTA, partial accumulators reduced in fixed order by the tile's owner) against
+    whole-tile scheduling: the same sums associated differently - fp32 rounding only - and bit-reproducible."""
+    sd, _ = models
+    msk = _fresh_model(sd, {"DSK_STREAM_K": "1"})
+    mwt = _fresh_model(sd, {"DSK_STREAM_K": "0"})
+    for B, T, seed in ((64, 160, 80), (9, 64, 81), (1, 16, 82), (33, 160, 83)):
+        x = O.make_input(B, T, seed=seed, scale=6.0).cuda()
+        with torch.no_grad():
+            a1, a2, b = msk(x).clone(), msk(x).clone(), mwt(x)
+        assert torch.equal(a1, a2), (B, T)
+        rel = ((a1 - b).norm(dim=1) / b.norm(dim=1)).max().item()
+        assert rel < 5e-4, (B, T, rel)     # 2e-4 measured at batch 64: fp32 reassociation -> occasional fp16 ulp flips

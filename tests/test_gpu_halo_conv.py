@@ -11,23 +11,27 @@ from deepspeaker_pytorch_b200 import _lib as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["two_ctas_per_sm", "one_cta_per_sm"])
+@pytest.fixture(scope="module", params=["one_cta_per_sm", "two_ctas_per_sm", "stream_k"])
 def hl(cuda_dev, request):
-    """Both CTA shapes of the halo kernel (csrc/conv3x3_halo.cuh): the 256-thread shape that shares an SM (default for
-    128-channel tiles) and the 384-thread one-per-SM shape; the handle reads DSK_SMALL_CTA when it is created."""
+    """The production shape of the halo kernel (384 threads, one CTA per SM, whole tiles) and its two opt-in variants
+    (csrc/conv3x3_halo.cuh): 256-thread CTAs sharing an SM, and stream-K scheduling; the handle reads the knobs when it
+    is created."""
     import os
 
     lib = L.load()
     h = ctypes.c_void_p()
-    old = os.environ.get("DSK_SMALL_CTA")
-    os.environ["DSK_SMALL_CTA"] = "1" if request.param == "two_ctas_per_sm" else "0"
+    knobs = {"DSK_SMALL_CTA": "1" if request.param == "two_ctas_per_sm" else "0",
+             "DSK_STREAM_K": "1" if request.param == "stream_k" else "0"}
+    old = {k: os.environ.get(k) for k in knobs}
+    os.environ.update(knobs)
     try:
         L.check(lib.dsk_create(ctypes.byref(h), 0, L.DSK_F16), "dsk_create")
     finally:
-        if old is None:
-            os.environ.pop("DSK_SMALL_CTA", None)
-        else:
-            os.environ["DSK_SMALL_CTA"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     yield lib, h
     lib.dsk_destroy(h)
 
