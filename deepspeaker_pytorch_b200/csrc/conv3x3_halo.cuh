@@ -120,7 +120,7 @@ struct HaloSmem {
   static constexpr int kBStageBytes = kTapsPerBox * N_TILE * 128;
   static constexpr int kTmemCols = kSmall ? 256 : (N_TILE == 256 ? 512 : 4 * N_TILE);
   static constexpr int kAccStages = kTmemCols / N_TILE;      // TMEM accumulators
-  static constexpr int kRowDstBytes = 2 * 128 * 8;                  // planar output: per-row destination, two tiles
+  static constexpr int kRowDstBytes = 2 * 2 * 128 * 8;              // planar output: per-row destination, two tiles x two epilogue groups
   static constexpr int kFixedBytes = kRowDstBytes + 512 + 1024;  // + barriers + alignment slack
   static int total(int a_stage_bytes, int a_stages, int b_stages, int stg_bufs, int res_bufs) {
     return a_stages * a_stage_bytes + b_stages * kBStageBytes + (stg_bufs + res_bufs) * kATileBytes + kFixedBytes;
@@ -276,14 +276,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmOut);
-    if (p.flags & CONV_RESIDUAL) tma_prefetch_desc(&tmRes);
     for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], EW);  // one arrive per epilogue warp
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&res_full[i], 1);
-      mbar_init(&res_empty[i], EW);
+      // a tile with >= 2 output chunks is shared by both epilogue groups (all EW warps arrive); a 64-channel tile
+      // belongs to ONE group of four warps (the groups alternate tiles)
+      mbar_init(&tmem_empty[i], (N_TILE >= 128) ? EW : 4);
     }
     fence_barrier_init();
   }
@@ -567,51 +564,41 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         first = false;
       }
     }
-  } else if (warp == 3) {
-    // ===================== residual prefetcher: one 128 x 64 tile per output chunk, two buffers =====================
-    if (!kSmall && (p.flags & CONV_RESIDUAL)) {
-      int rb = 0;
-      uint32_t rph = 0;
-      int cur = seg_begin();
-      int tile, ub, ue;
-      while (next_seg(cur, tile, ub, ue)) {
-        if (ub > 0) continue;  // a later part of a tile: no epilogue here, its owner adds the residual
-        int c0, q0;
-        decode(tile, c0, q0);
-        for (int j = 0; j < kChunksOut; ++j) {
-          mbar_wait(&res_empty[rb], rph ^ 1);
-          if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&res_full[rb], kATileBytes);
-            tma_load_2d(smem_res + rb * kATileBytes, &tmRes, &res_full[rb], c0 + j * 64, q0);
-          }
-          __syncwarp();
-          if (++rb == p.res_bufs) {
-            rb = 0;
-            rph ^= 1;
-          }
-        }
-      }
-    }
   } else if (warp >= 4) {
-    // ===================== epilogue: EW warps; thread = one padded output position x 32 channels at a time ==========
-    // EW = 8: warp (ew, half) owns 32 of the 64 channels of every chunk; EW = 4: warp ew walks both halves.
+    // ===================== epilogue: EW / 4 independent GROUPS of four warps ===========================================
+    // A group = 128 threads = the 128 TMEM lanes (thread = one padded output position).  It owns one staging tile, one
+    // named barrier and its own TMA-store queue, and takes 64-channel output chunks whole (two 32-column TMEM loads):
+    //   tiles of >= 128 channels: group g takes chunks g, g + 2, ... of EVERY tile (both groups work on a tile at once);
+    //   64-channel tiles: the groups alternate tiles (two tiles' epilogues in flight).
+    // Round 1 ran all eight warps in lockstep through one chunk at a time (two 256-thread barriers per chunk, one
+    // staging tile): ~2700 cycles per chunk, 5400 per 128-channel tile, of which ~900 per chunk were barrier / load /
+    // store latency every warp sat through (profiles/r02_trace_halo.txt).  The residual is read straight from global
+    // memory (it was written two kernels ago and sits in L2), 64 bytes per thread one step ahead of their use: no
+    // residual tiles through shared memory, whose port the MMA operand fetch saturates.
+    constexpr int kGroups = EW / 4;
+    const int g = (warp - 4) >> 2;
     const int ew = (warp - 4) & 3;          // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const int half0 = kSmall ? 0 : (warp - 4) >> 2;
-    constexpr int kHalves = kSmall ? 2 : 1;
     const int row = ew * 32 + lane;
-    const int etid = threadIdx.x - 128;
+    const int gtid = (threadIdx.x - 128) & 127;
+    const int etid = threadIdx.x - 128;     // group 0's thread 0 carries the trace stamps
+    const int bar_id = 1 + g;
+    constexpr bool kShareTile = kChunksOut >= 2 || kGroups == 1;  // every group works on every tile
+    const int j_first = (kChunksOut >= 2) ? g : 0;
     const bool has_res = (p.flags & CONV_RESIDUAL) != 0;
     const bool do_clip = (p.flags & CONV_CLIP) != 0;
     const int rows_real_end = p.N * (p.H + 1) + 1;  // first row index past the last image
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int rb = 0;
-    uint32_t rph = 0;
-    int buf = 0;
-    int ecount = 0;
+    uint8_t* stg = smem_stg + g * kATileBytes;
+    uint16_t** my_row_dst = row_dst + g * 256;
+    int nseg = 0;     // segments of this CTA so far (all groups count alike): accumulator stage and phase follow from it
+    int ecount = 0;   // tiles this group has written out
     int cur = seg_begin();
     int tile, ub, ue;
     while (next_seg(cur, tile, ub, ue)) {
+      const int acc = nseg % kAcc;
+      const uint32_t acc_phase = (nseg / kAcc) & 1;
+      const bool mine = kShareTile || (nseg & 1) == g;
+      ++nseg;
+      if (!mine) continue;
       int c0, q0;
       decode(tile, c0, q0);
       if (SK && ub > 0) {
@@ -620,14 +607,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         tc_fence_after();
         float4* dst = reinterpret_cast<float4*>(p.sk_partial) + static_cast<size_t>(blockIdx.x) * (N_TILE / 4) * kTileM + row;
 #pragma unroll 1
-        for (int j = 0; j < kChunksOut; ++j) {
+        for (int j = j_first; j < kChunksOut; j += kGroups) {
 #pragma unroll
-          for (int hx = 0; hx < kHalves; ++hx) {
-            const int half = kSmall ? hx : half0;
+          for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64 + half * 32, v);
             tmem_ld_wait();
-            float4* d4 = dst + static_cast<size_t>(j * 16 + half * 8) * kTileM;   // 4-column group g of the tile at dst[g * 128]
+            float4* d4 = dst + static_cast<size_t>(j * 16 + half * 8) * kTileM;   // 4-column group q of the tile at dst[q * 128]
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq)
               d4[qq * kTileM] = make_float4(__uint_as_float(v[4 * qq]), __uint_as_float(v[4 * qq + 1]),
@@ -638,12 +624,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        named_bar_sync(1, kEpiThreads);  // every thread's partial rows are written and fenced
+        named_bar_sync(3, kEpiThreads);  // every thread's partial rows (both groups) are written and fenced
         if (etid == 0) st_release_gpu(p.sk_flags + blockIdx.x, 1);
-        if (++acc == kAcc) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
         continue;
       }
       // stream-K: the head of a cut tile owns its epilogue; the parts live in the next CTAs' ranges (each CTA's range
@@ -662,29 +644,28 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       const bool junk = (cc == 0) || (R - img * (p.H + 1) == 0) || (R >= rows_real_end);
       // parity-planar destination of this position (only when the consumer is a stride-2 conv): pixel (n, h, w) ->
       // plane (h&1, w&1), padded position of (n, h>>1, w>>1) on the half-resolution grid
-      uint16_t* planar_row = nullptr;
-      if (p.out_planar && !junk) {
-        const int n = (R - 1 >= 0) ? img : 0;  // R = n*(H+1) + h + 1 with h < H  =>  img == n for real rows
-        const int hh = R - 1 - n * (p.H + 1), ww = cc - 1;
-        const int H2 = p.H >> 1, W2 = p.W >> 1;
-        const long q2 = static_cast<long>(n * (H2 + 1) + (hh >> 1) + 1) * (W2 + 1) + (ww >> 1) + 1;
-        const long plane = (hh & 1) * 2 + (ww & 1);
-        planar_row = p.out_ptr + (plane * p.out_plane_positions + q2) * p.out_C + c0;
+      if (p.out_planar) {
+        uint16_t* planar_row = nullptr;
+        if (!junk) {
+          const int n = (R - 1 >= 0) ? img : 0;  // R = n*(H+1) + h + 1 with h < H  =>  img == n for real rows
+          const int hh = R - 1 - n * (p.H + 1), ww = cc - 1;
+          const int H2 = p.H >> 1, W2 = p.W >> 1;
+          const long q2 = static_cast<long>(n * (H2 + 1) + (hh >> 1) + 1) * (W2 + 1) + (ww >> 1) + 1;
+          const long plane = (hh & 1) * 2 + (ww & 1);
+          planar_row = p.out_ptr + (plane * p.out_plane_positions + q2) * p.out_C + c0;
+        }
+        // published before this tile's first chunk barrier; two tables per group because a fast thread may enter the
+        // next tile while others still copy this one out
+        my_row_dst[(ecount & 1) * 128 + row] = planar_row;
       }
-      // published before the first chunk barrier of this tile; two tables because a fast thread may enter the next
-      // tile while others still copy this one out
-      if (p.out_planar && half0 == 0) row_dst[(ecount & 1) * 128 + row] = planar_row;
-      // EW = 4: the residual comes straight from global memory (it was written two kernels ago and sits in L2); the
-      // 64 bytes of the NEXT (chunk, half) are fetched one step ahead so that their latency hides under this step's math
+      // residual: the 64 bytes of the first (chunk, half) now, every later one a step ahead of its use
       const uint16_t* res_g = nullptr;
       uint4 rn[4] = {};
-      if constexpr (kSmall) {
-        if (has_res) {
-          res_g = p.res_ptr + static_cast<size_t>(q) * p.cout + c0;
-          const uint4* g4 = reinterpret_cast<const uint4*>(res_g);
+      if (has_res) {
+        res_g = p.res_ptr + static_cast<size_t>(q) * p.cout + c0;
+        const uint4* g4 = reinterpret_cast<const uint4*>(res_g + j_first * 64);
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) rn[qq] = __ldg(g4 + qq);
-        }
+        for (int qq = 0; qq < 4; ++qq) rn[qq] = __ldg(g4 + qq);
       }
       if (etid == 0) DSK_TRACE(2, ecount * 8 + 0);
       if (p.late_trigger && (sk ? cur >= u_hi : cur >= num_tiles)) pdl_launch_dependents();
@@ -701,9 +682,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
               if (clock64() - t_wait > (1ll << 32)) __trap();
             }
         }
-        named_bar_sync(1, kEpiThreads);
+        named_bar_sync(3, kEpiThreads);
         const float4* s4 = reinterpret_cast<const float4*>(p.sk_partial) +
-                           (static_cast<size_t>(blockIdx.x + 1) * (N_TILE / 4) + (kSmall ? 0 : half0) * 8) * kTileM + row;
+                           (static_cast<size_t>(blockIdx.x + 1) * (N_TILE / 4) + j_first * 16) * kTileM + row;
 #pragma unroll
         for (int qq = 0; qq < 8; ++qq) pre[qq] = __ldcg(s4 + qq * kTileM);
       }
@@ -711,25 +692,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
       tc_fence_after();
       if (etid == 0) DSK_TRACE(2, ecount * 8 + 1);
 #pragma unroll 1
-      for (int j = 0; j < kChunksOut; ++j) {
-        uint8_t* stg = smem_stg + buf * kATileBytes;
-        if (etid == 0) {  // the TMA store that last used this staging buffer must have finished reading it
-          if (p.stg_bufs == 2) tma_store_wait_read<1>();
-          else tma_store_wait_read<0>();
-        }
-        named_bar_sync(1, kEpiThreads);
+      for (int j = j_first; j < kChunksOut; j += kGroups) {
+        if (gtid == 0) tma_store_wait_read<0>();  // the group's previous TMA store has finished reading the staging tile
+        named_bar_sync(bar_id, 128);
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 2);
         uint8_t* my_row = stg + row * 128;
 #pragma unroll
-        for (int hx = 0; hx < kHalves; ++hx) {
-          const int half = kSmall ? hx : half0;
+        for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * N_TILE + j * 64 + half * 32, v);
           uint4 rc[4] = {rn[0], rn[1], rn[2], rn[3]};
-          if constexpr (kSmall) {
-            const int nxt = (j * 2 + hx + 1);  // next (chunk, half) of this tile, if any
-            if (has_res && nxt < 2 * kChunksOut) {
-              const uint4* g4 = reinterpret_cast<const uint4*>(res_g + (nxt >> 1) * 64 + (nxt & 1) * 32);
+          if (has_res) {  // next (chunk, half) of this group, if any
+            const int nj = half == 0 ? j : j + kGroups;
+            if (nj < kChunksOut) {
+              const uint4* g4 = reinterpret_cast<const uint4*>(res_g + nj * 64 + (half ^ 1) * 32);
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq) rn[qq] = __ldg(g4 + qq);
             }
@@ -741,7 +717,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
                                  (static_cast<size_t>(blockIdx.x + c) * (N_TILE / 4) + j * 16 + half * 8) * kTileM + row;
 #pragma unroll
               for (int qq = 0; qq < 8; ++qq) {
-                const float4 t4 = (c == 1 && j == 0 && hx == 0) ? pre[qq] : __ldcg(s4 + qq * kTileM);
+                const float4 t4 = (c == 1 && j == j_first && half == 0) ? pre[qq] : __ldcg(s4 + qq * kTileM);
                 v[4 * qq + 0] = __float_as_uint(__uint_as_float(v[4 * qq + 0]) + t4.x);
                 v[4 * qq + 1] = __float_as_uint(__uint_as_float(v[4 * qq + 1]) + t4.y);
                 v[4 * qq + 2] = __float_as_uint(__uint_as_float(v[4 * qq + 2]) + t4.z);
@@ -749,12 +725,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
               }
             }
           }
-          if (etid == 0 && j == 0 && hx == 0) DSK_TRACE(2, ecount * 8 + 3);
-          if constexpr (!kSmall) {
-            if (has_res) mbar_wait(&res_full[rb], rph);
-          }
-          if (etid == 0 && j == 0 && hx == 0) DSK_TRACE(2, ecount * 8 + 4);
-          const uint8_t* res_row = smem_res + rb * kATileBytes + row * 128;
+          if (etid == 0 && j == 0 && half == 0) DSK_TRACE(2, ecount * 8 + 3);
           const int cbase = c0 + j * 64 + half * 32;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
@@ -768,12 +739,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[qq * 8 + e]), scv[e], biv[e]);
-            const int chunk16 = ((half * 4 + qq) ^ (row & 7)) << 4;  // 16-byte slot inside the swizzled 128-byte row
-            uint4* slot = reinterpret_cast<uint4*>(my_row + chunk16);
             if (has_res) {
-              uint4 r4;
-              if constexpr (kSmall) r4 = rc[qq];
-              else r4 = *reinterpret_cast<const uint4*>(res_row + chunk16);
+              const uint4 r4 = rc[qq];
               float2 t;
               t = unpack2<BF16>(r4.x); f[0] += t.x; f[1] += t.y;
               t = unpack2<BF16>(r4.y); f[2] += t.x; f[3] += t.y;
@@ -790,55 +757,45 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
             o.z = pack2<BF16>(f[4], f[5]);
             o.w = pack2<BF16>(f[6], f[7]);
             if (junk) o = make_uint4(0u, 0u, 0u, 0u);  // pad positions stay zero
-            *slot = o;
+            const int chunk16 = ((half * 4 + qq) ^ (row & 7)) << 4;  // 16-byte slot inside the swizzled 128-byte row
+            *reinterpret_cast<uint4*>(my_row + chunk16) = o;
           }
         }
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 5);
         fence_proxy_async_smem();
-        if (!kSmall && has_res) {  // residual buffer consumed: hand it back to the prefetcher
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&res_empty[rb]);
-          if (++rb == p.res_bufs) {
-            rb = 0;
-            rph ^= 1;
-          }
-        }
-        named_bar_sync(1, kEpiThreads);
+        named_bar_sync(bar_id, 128);
         if (!p.out_planar) {
-          if (etid == 0) {
+          if (gtid == 0) {
             tma_store_2d(&tmOut, stg, c0 + j * 64, q0);
             tma_store_commit();
           }
         } else {
           // parity-planar destination: rows scatter over four planes, so no TMA box; 8 lanes copy one 128-byte row
-          // (full lines per warp store), 128 / (threads / 8) rows per thread
-          const int chunk = etid & 7;
-          constexpr int kRowsPerPass = kEpiThreads / 8;
+          // (full lines per warp store), 8 rows per thread
+          const int chunk = gtid & 7;
 #pragma unroll
-          for (int i = 0; i < 128 / kRowsPerPass; ++i) {
-            const int rr = i * kRowsPerPass + (etid >> 3);
-            uint16_t* d = row_dst[(ecount & 1) * 128 + rr];
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 16 + (gtid >> 3);
+            uint16_t* d = my_row_dst[(ecount & 1) * 128 + rr];
             if (d != nullptr)
               *reinterpret_cast<uint4*>(d + j * 64 + chunk * 8) =
                   *reinterpret_cast<const uint4*>(stg + rr * 128 + ((chunk ^ (rr & 7)) << 4));
           }
         }
         if (etid == 0 && j == 0) DSK_TRACE(2, ecount * 8 + 6);
-        if (++buf == p.stg_bufs) buf = 0;
       }
-      if (SK && n_parts > 0 && etid == 0)  // every thread passed the last chunk's barrier after reading the partials
-        for (int c = 1; c <= n_parts; ++c) p.sk_flags[blockIdx.x + c] = 0;
+      if (SK && n_parts > 0) {  // both groups have read the partials: the flags can go back to zero
+        named_bar_sync(3, kEpiThreads);
+        if (etid == 0)
+          for (int c = 1; c <= n_parts; ++c) p.sk_flags[blockIdx.x + c] = 0;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (etid == 0) DSK_TRACE(2, ecount * 8 + 7);
       ++ecount;
-      if (++acc == kAcc) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
     }
-    if (etid == 0) tma_store_wait_all<0>();
+    if (gtid == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

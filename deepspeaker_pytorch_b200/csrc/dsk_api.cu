@@ -745,7 +745,6 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
   {
     const int halo_rows = 128 + 2 * W + 4;
     p.a_stage_bytes = (halo_rows * 128 + 1023) / 1024 * 1024;
-    const bool has_res = (flags & dsk::CONV_RESIDUAL) != 0;
     const int b_bytes = tpb * n_tile * 128;
     const int fixed = dsk::HaloSmem<128>::kFixedBytes;  // the same for every tile width
     if (small) {
@@ -760,22 +759,18 @@ int build_halo(const dsk_handle_s* h, HaloLaunch* L, const void* in, const void*
       p.b_stages = nb;
       L->smem = p.a_stages * p.a_stage_bytes + p.b_stages * b_bytes + p.stg_bufs * 16384 + fixed;
     } else {
-    const int limit = 227 * 1024;
-    p.a_stages = n_tile == 64 ? 3 : 2;
-    p.stg_bufs = 2;
-    p.res_bufs = has_res ? 2 : 0;
-    auto fit_b = [&]() { return (limit - fixed - p.a_stages * p.a_stage_bytes - (p.stg_bufs + p.res_bufs) * 16384) / b_bytes; };
-    int nb = fit_b();
-    if (nb < 3 && !p.b_resident) {  // trade buffers for a third weight stage
-      if (has_res) p.res_bufs = 1;
-      p.stg_bufs = 1;
-      nb = fit_b();
-      if (nb < 3) p.stg_bufs = 2, p.res_bufs = has_res ? 2 : 0, nb = fit_b();
-    }
-    p.b_stages = nb > dsk::kHaloMaxStages ? dsk::kHaloMaxStages : nb;
-    if (p.b_resident) p.b_stages = 3;
-    if (p.b_stages < 2) return fail(DSK_ERR_INVALID, "halo conv: shared memory does not fit");
-    L->smem = p.a_stages * p.a_stage_bytes + p.b_stages * b_bytes + (p.stg_bufs + p.res_bufs) * 16384 + fixed;
+      // one CTA per SM: two epilogue groups with one staging tile each; the residual is read from global memory
+      // (HaloParams::res_ptr), so everything else goes to the operand rings - weight boxes first (48 KB each at
+      // N_TILE = 128: the latency-critical stream)
+      const int limit = 227 * 1024;
+      p.a_stages = n_tile == 64 ? 3 : 2;
+      p.stg_bufs = 2;
+      p.res_bufs = 0;
+      int nb = (limit - fixed - p.a_stages * p.a_stage_bytes - p.stg_bufs * 16384) / b_bytes;
+      p.b_stages = nb > dsk::kHaloMaxStages ? dsk::kHaloMaxStages : nb;
+      if (p.b_resident) p.b_stages = 3;
+      if (p.b_stages < 2) return fail(DSK_ERR_INVALID, "halo conv: shared memory does not fit");
+      L->smem = p.a_stages * p.a_stage_bytes + p.b_stages * b_bytes + p.stg_bufs * 16384 + fixed;
     }
   }
   const int num_tiles = p.tiles_m * p.tiles_c;

@@ -38,4 +38,5 @@ for k in range(12):
     e = [int(v) - t0 if v > 0 else None for v in t[2, 8 * k:8 * k + 8]]
     if m[0] is None: break
     d = [e[i + 1] - e[i] if (e[i] is not None and e[i + 1] is not None) else None for i in range(7)]
+    if e[0] is None or m[2] is None: break
     print(f"tile {k:2d} MMA issue {m[2]-m[1]:5d} | EPI start {e[0]:7d} deltas " + " ".join(f"{names[i+1]}={d[i]}" for i in range(7)))
