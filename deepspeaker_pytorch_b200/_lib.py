@@ -164,6 +164,14 @@ SIGNATURES = {
                                    c_int64, c_float, c_void_p, c_void_p]),
     "dsk_set_defer_running_stats": (c_int32, [c_void_p, c_int32]),
     "dsk_train_ctx_commit_stats": (c_int32, [c_void_p, c_void_p, c_void_p]),
+    "dsk_pipeline_create": (c_int32, [POINTER(c_void_p), c_void_p, c_int32, c_int32]),
+    "dsk_pipeline_destroy": (c_int32, [c_void_p]),
+    "dsk_pipeline_submit": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_int64)]),
+    "dsk_pipeline_submit_device": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, POINTER(c_int64)]),
+    "dsk_pipeline_join": (c_int32, [c_void_p, c_void_p]),
+    "dsk_pipeline_wait": (c_int32, [c_void_p, c_int64]),
+    "dsk_pipeline_sync": (c_int32, [c_void_p]),
+    "dsk_pipeline_lane_stream": (c_int32, [c_void_p, c_int32, POINTER(c_void_p)]),
     "dsk_threshold_counts": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 

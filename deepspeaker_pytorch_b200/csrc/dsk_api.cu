@@ -2195,4 +2195,211 @@ int32_t dsk_threshold_counts(const float* dist, const uint8_t* same, int32_t P, 
   return DSK_OK;
 }
 
+
+// =================================================================================================
+// Serving pipeline (dsk_pipeline_*): the reference's test() loop (train_triplet.py:337-350) moves a batch to the GPU,
+// runs the model and pulls the result back, all on one stream and all driven from Python.  Here one call per batch
+// queues: H2D copy of the pinned input into a device slot (copy stream) -> eval forward on the next compute lane
+// (its own handle / activation workspace; lanes share one packed weight image) -> D2H copy of the embeddings (second
+// copy stream).  Ordering is by CUDA events only; the host never blocks in submit, and the whole submit is ~12 CUDA
+// runtime calls issued from C++ (the Python pipeline spent 0.12-0.18 ms per batch on the host against a 0.2 ms GPU step).
+// =================================================================================================
+struct dsk_pipeline_s {
+  dsk_handle primary = nullptr;
+  int device = 0;
+  int lanes = 0, depth = 0;
+  std::vector<dsk_handle> handle;          // [lanes], all owned: each borrows the primary's packed weights
+  std::vector<cudaStream_t> lane_stream;   // [lanes]
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  struct Slot {
+    float* x = nullptr;
+    float* emb = nullptr;
+    size_t x_bytes = 0, emb_bytes = 0;
+    cudaEvent_t h2d_done = nullptr, fwd_done = nullptr, d2h_done = nullptr;
+    long long ticket = -1;
+  };
+  std::vector<Slot> slot;                  // [lanes * depth]
+  std::vector<cudaEvent_t> join_ev;        // [lanes]
+  cudaEvent_t in_ev = nullptr;
+  long long next = 0;
+};
+
+static int pipeline_slot_fit(dsk_pipeline_s* p, dsk_pipeline_s::Slot& s, size_t xb, size_t eb) {
+  if (s.x_bytes < xb) {
+    if (s.x) {
+      CUDA_TRY(cudaEventSynchronize(s.fwd_done));  // the forward that read the old buffer
+      CUDA_TRY(cudaFree(s.x));
+    }
+    s.x = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&s.x), xb));
+    s.x_bytes = xb;
+  }
+  if (s.emb_bytes < eb) {
+    if (s.emb) {
+      CUDA_TRY(cudaEventSynchronize(s.d2h_done));
+      CUDA_TRY(cudaFree(s.emb));
+    }
+    s.emb = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&s.emb), eb));
+    s.emb_bytes = eb;
+  }
+  (void)p;
+  return DSK_OK;
+}
+
+int32_t dsk_pipeline_create(dsk_pipeline* out, dsk_handle primary, int32_t lanes, int32_t depth) {
+  if (!out) return fail(DSK_ERR_INVALID, "dsk_pipeline_create: out is null");
+  int rc = check_handle(primary);
+  if (rc) return rc;
+  if (primary->src) return fail(DSK_ERR_INVALID, "dsk_pipeline_create: the primary handle must own its weights");
+  if (lanes < 1 || lanes > 8 || depth < 1 || depth > 16) return fail(DSK_ERR_INVALID, "dsk_pipeline_create: lanes 1..8, depth 1..16");
+  dsk_pipeline_s* p = new dsk_pipeline_s();
+  p->primary = primary;
+  p->device = primary->device;
+  p->lanes = lanes;
+  p->depth = depth;
+  p->handle.assign(lanes, nullptr);
+  p->lane_stream.assign(lanes, nullptr);
+  p->join_ev.assign(lanes, nullptr);
+  p->slot.resize(static_cast<size_t>(lanes) * depth);
+  auto bail = [&](int code) {
+    dsk_pipeline_destroy(p);
+    return code;
+  };
+  for (int i = 0; i < lanes; ++i) {  // the primary itself stays free for the caller's own stream
+    rc = dsk_create(&p->handle[i], primary->device, primary->bf16 ? DSK_BF16 : DSK_F16);
+    if (rc) return bail(rc);
+    rc = dsk_share_weights(p->handle[i], primary);
+    if (rc) return bail(rc);
+  }
+  for (int i = 0; i < lanes; ++i) {
+    if (cudaStreamCreateWithFlags(&p->lane_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->join_ev[i], cudaEventDisableTiming) != cudaSuccess)
+      return bail(fail(DSK_ERR_CUDA, "dsk_pipeline_create: stream / event creation failed"));
+  }
+  if (cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->in_ev, cudaEventDisableTiming) != cudaSuccess)
+    return bail(fail(DSK_ERR_CUDA, "dsk_pipeline_create: stream creation failed"));
+  for (auto& s : p->slot) {
+    if (cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fwd_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming) != cudaSuccess)
+      return bail(fail(DSK_ERR_CUDA, "dsk_pipeline_create: event creation failed"));
+  }
+  *out = p;
+  return DSK_OK;
+}
+
+int32_t dsk_pipeline_destroy(dsk_pipeline p) {
+  if (!p) return DSK_OK;
+  cudaSetDevice(p->device);
+  for (cudaStream_t s : p->lane_stream)
+    if (s) cudaStreamSynchronize(s);
+  if (p->h2d) cudaStreamSynchronize(p->h2d);
+  if (p->d2h) cudaStreamSynchronize(p->d2h);
+  for (dsk_handle h : p->handle)
+    if (h) dsk_destroy(h);
+  for (auto& s : p->slot) {
+    cudaFree(s.x);
+    cudaFree(s.emb);
+    if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+    if (s.fwd_done) cudaEventDestroy(s.fwd_done);
+    if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+  }
+  for (cudaEvent_t e : p->join_ev)
+    if (e) cudaEventDestroy(e);
+  if (p->in_ev) cudaEventDestroy(p->in_ev);
+  for (cudaStream_t s : p->lane_stream)
+    if (s) cudaStreamDestroy(s);
+  if (p->h2d) cudaStreamDestroy(p->h2d);
+  if (p->d2h) cudaStreamDestroy(p->d2h);
+  delete p;
+  return DSK_OK;
+}
+
+int32_t dsk_pipeline_submit(dsk_pipeline p, const float* x_host, int32_t B, int32_t T, float* emb_host, int64_t* ticket) {
+  if (!p || !x_host || !emb_host || B <= 0) return fail(DSK_ERR_INVALID, "dsk_pipeline_submit: bad arguments");
+  if (T < 16 || T % 16) return fail(DSK_ERR_INVALID, "dsk_pipeline_submit: T must be a positive multiple of 16 (got %d)", T);
+  CUDA_TRY(cudaSetDevice(p->device));
+  const long long i = p->next;
+  const int lane = static_cast<int>(i % p->lanes);
+  dsk_pipeline_s::Slot& s = p->slot[static_cast<size_t>(i % (static_cast<long long>(p->lanes) * p->depth))];
+  const size_t xb = static_cast<size_t>(B) * T * 64 * sizeof(float);
+  const size_t eb = static_cast<size_t>(B) * p->primary->emb * sizeof(float);
+  int rc = pipeline_slot_fit(p, s, xb, eb);
+  if (rc) return rc;
+  cudaStream_t ls = p->lane_stream[lane];
+  if (s.ticket >= 0) CUDA_TRY(cudaStreamWaitEvent(p->h2d, s.fwd_done, 0));  // the forward that read this slot's input
+  CUDA_TRY(cudaMemcpyAsync(s.x, x_host, xb, cudaMemcpyHostToDevice, p->h2d));
+  CUDA_TRY(cudaEventRecord(s.h2d_done, p->h2d));
+  CUDA_TRY(cudaStreamWaitEvent(ls, s.h2d_done, 0));
+  if (s.ticket >= 0) CUDA_TRY(cudaStreamWaitEvent(ls, s.d2h_done, 0));       // the copy that read this slot's embeddings
+  rc = dsk_rescnn_forward(p->handle[lane], s.x, B, T, s.emb, DSK_EVAL, ls);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(s.fwd_done, ls));
+  CUDA_TRY(cudaStreamWaitEvent(p->d2h, s.fwd_done, 0));
+  CUDA_TRY(cudaMemcpyAsync(emb_host, s.emb, eb, cudaMemcpyDeviceToHost, p->d2h));
+  CUDA_TRY(cudaEventRecord(s.d2h_done, p->d2h));
+  s.ticket = i;
+  p->next = i + 1;
+  if (ticket) *ticket = i;
+  return DSK_OK;
+}
+
+int32_t dsk_pipeline_submit_device(dsk_pipeline p, const float* x_dev, int32_t B, int32_t T, float* emb_dev, void* after_stream,
+                                   int64_t* ticket) {
+  if (!p || !x_dev || !emb_dev || B <= 0) return fail(DSK_ERR_INVALID, "dsk_pipeline_submit_device: bad arguments");
+  CUDA_TRY(cudaSetDevice(p->device));
+  const long long i = p->next;
+  const int lane = static_cast<int>(i % p->lanes);
+  cudaStream_t ls = p->lane_stream[lane];
+  // the inputs (and the output buffer's previous use) are ordered on the caller's stream
+  CUDA_TRY(cudaEventRecord(p->in_ev, static_cast<cudaStream_t>(after_stream)));
+  CUDA_TRY(cudaStreamWaitEvent(ls, p->in_ev, 0));
+  int rc = dsk_rescnn_forward(p->handle[lane], x_dev, B, T, emb_dev, DSK_EVAL, ls);
+  if (rc) return rc;
+  p->next = i + 1;
+  if (ticket) *ticket = i;
+  return DSK_OK;
+}
+
+int32_t dsk_pipeline_join(dsk_pipeline p, void* stream) {
+  if (!p) return fail(DSK_ERR_INVALID, "dsk_pipeline_join: null pipeline");
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < p->lanes; ++i) {
+    CUDA_TRY(cudaEventRecord(p->join_ev[i], p->lane_stream[i]));
+    CUDA_TRY(cudaStreamWaitEvent(st, p->join_ev[i], 0));
+  }
+  return DSK_OK;
+}
+
+int32_t dsk_pipeline_wait(dsk_pipeline p, int64_t ticket) {
+  if (!p || ticket < 0 || ticket >= p->next) return fail(DSK_ERR_INVALID, "dsk_pipeline_wait: unknown ticket");
+  CUDA_TRY(cudaSetDevice(p->device));
+  dsk_pipeline_s::Slot& s = p->slot[static_cast<size_t>(ticket % (static_cast<long long>(p->lanes) * p->depth))];
+  if (s.ticket == ticket) CUDA_TRY(cudaEventSynchronize(s.d2h_done));
+  // a ticket whose slot has been reused was completed before the reuse was allowed to start (or was a device submit)
+  else if (s.ticket < ticket) {
+    for (cudaStream_t ls : p->lane_stream) CUDA_TRY(cudaStreamSynchronize(ls));
+  }
+  return DSK_OK;
+}
+
+int32_t dsk_pipeline_sync(dsk_pipeline p) {
+  if (!p) return fail(DSK_ERR_INVALID, "dsk_pipeline_sync: null pipeline");
+  CUDA_TRY(cudaSetDevice(p->device));
+  CUDA_TRY(cudaStreamSynchronize(p->h2d));
+  for (cudaStream_t ls : p->lane_stream) CUDA_TRY(cudaStreamSynchronize(ls));
+  CUDA_TRY(cudaStreamSynchronize(p->d2h));
+  return DSK_OK;
+}
+
+int32_t dsk_pipeline_lane_stream(dsk_pipeline p, int32_t lane, void** stream_out) {
+  if (!p || lane < -2 || lane >= p->lanes || !stream_out) return fail(DSK_ERR_INVALID, "dsk_pipeline_lane_stream: bad arguments");
+  *stream_out = lane == -1 ? p->h2d : lane == -2 ? p->d2h : p->lane_stream[lane];
+  return DSK_OK;
+}
+
 }  // extern "C"

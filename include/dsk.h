@@ -67,6 +67,7 @@ typedef struct {
 
 typedef struct dsk_handle_s* dsk_handle;
 typedef struct dsk_train_ctx_s* dsk_train_ctx; /* what one train-mode forward saved for its backward */
+typedef struct dsk_pipeline_s* dsk_pipeline;   /* serving pipeline: copy streams + compute lanes around one weight image */
 
 const char* dsk_last_error(void);
 int32_t dsk_version(void);
@@ -244,6 +245,26 @@ int32_t dsk_cross_entropy_bwd(const float* logits, const int64_t* labels, const 
 int32_t dsk_adagrad_step(float* param, const float* grad, float* state_sum, int64_t n, double lr, double lr_decay,
                          double weight_decay, double eps, int64_t step, float grad_mult, const float* grad_denom,
                          void* stream);
+
+/* Serving pipeline for the reference's test() loop (/root/reference/train_triplet.py:337-350: batch to the GPU, model(x),
+ * result back - serialised on one stream there).  `primary` owns the weights (dsk_load_weights); the pipeline adds
+ * `lanes` handles that borrow them (dsk_share_weights; `primary` stays free for its caller), one compute stream per lane and two copy streams, and keeps depth*lanes device
+ * slots.  dsk_pipeline_submit queues, without blocking the host: H2D of the PINNED input batch (B,1,T,64) fp32 -> eval forward
+ * on the next lane -> D2H of the (B,E) embeddings into the PINNED output; *ticket identifies the batch.  Both host buffers
+ * are accessed asynchronously: leave x_host / emb_host alone until dsk_pipeline_wait(ticket) (blocks the host until that
+ * batch's output is complete) or dsk_pipeline_sync.
+ * dsk_pipeline_submit_device runs device-resident batches through the same lanes (inputs ordered after `after_stream`);
+ * dsk_pipeline_join makes `stream` wait for everything submitted so far; dsk_pipeline_lane_stream returns the cudaStream_t of
+ * compute lane 0..lanes-1 (-1: the H2D copy stream, -2: the D2H copy stream) for event timing.  One thread drives a pipeline. */
+int32_t dsk_pipeline_create(dsk_pipeline* out, dsk_handle primary, int32_t lanes, int32_t depth);
+int32_t dsk_pipeline_destroy(dsk_pipeline p);
+int32_t dsk_pipeline_submit(dsk_pipeline p, const float* x_host, int32_t B, int32_t T, float* emb_host, int64_t* ticket);
+int32_t dsk_pipeline_submit_device(dsk_pipeline p, const float* x_dev, int32_t B, int32_t T, float* emb_dev, void* after_stream,
+                                   int64_t* ticket);
+int32_t dsk_pipeline_join(dsk_pipeline p, void* stream);
+int32_t dsk_pipeline_wait(dsk_pipeline p, int64_t ticket);
+int32_t dsk_pipeline_sync(dsk_pipeline p);
+int32_t dsk_pipeline_lane_stream(dsk_pipeline p, int32_t lane, void** stream_out);
 
 /* Threshold sweep of the verification metric (/root/reference/eval_metrics.py:16-37 calculate_roc, :53-88 calculate_val /
  * calculate_val_far; called from train_triplet.py:361): for every threshold t (double, as numpy's arange yields them)

@@ -101,3 +101,37 @@ def test_shape_change_mid_stream_keeps_earlier_batches_intact(model):
         torch.cuda.synchronize()
         for i, x in enumerate(seq):
             assert torch.equal(outs[i], model(x.cuda())), i
+
+
+def test_tickets_and_frozen_mode(model):
+    """embed() returns a ticket; wait(ticket) blocks the host until that batch's pinned output is complete (later
+    batches may still be in flight).  check_every=0 freezes the packed weights until refresh()."""
+    pipe = dsk.EmbeddingPipeline(model, lanes=2, depth=2, check_every=0)
+    xs = [O.make_input(5, 32, seed=400 + i, scale=3.0) for i in range(9)]     # 9 batches > lanes * depth slots
+    xh = [x.pin_memory() for x in xs]
+    oh = [torch.zeros(5, 512).pin_memory() for _ in xs]
+    tickets = [pipe.embed(a, b) for a, b in zip(xh, oh)]
+    assert tickets == list(range(tickets[0], tickets[0] + 9))
+    pipe.wait(tickets[2])
+    with torch.no_grad():
+        assert torch.equal(oh[2], model(xs[2].cuda()).cpu())
+    pipe.wait(tickets[0])                  # a ticket whose slot was reused since: already complete
+    pipe.synchronize()
+    with torch.no_grad():
+        for i in (0, 8):
+            assert torch.equal(oh[i], model(xs[i].cuda()).cpu()), i
+        model.model.conv3.weight.mul_(1.25)        # a PACKED parameter (the fc bias is read in place, not packed)
+        try:
+            stale = torch.zeros(5, 512).pin_memory()
+            pipe.wait(pipe.embed(xh[0], stale))
+            assert torch.equal(stale, oh[0])                       # frozen: still the old weights
+            pipe.refresh()
+            fresh = torch.zeros(5, 512).pin_memory()
+            pipe.wait(pipe.embed(xh[0], fresh))
+            assert torch.equal(fresh, model(xs[0].cuda()).cpu()) and not torch.equal(fresh, stale)
+        finally:
+            model.model.conv3.weight.div_(1.25)
+    with pytest.raises(RuntimeError):
+        pipe.embed(xs[0], oh[0])                                   # not pinned
+    with pytest.raises(RuntimeError):
+        pipe.wait(10 ** 9)

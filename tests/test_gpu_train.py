@@ -289,3 +289,38 @@ def test_train_step_helper_runs_both_branches_like_the_oracle(cuda_dev, golden_d
     assert rA["ce"] is None and rA["selected"] == int(B) and opt.step_count == 2 and torch.isfinite(rA["loss"])
     with pytest.raises(RuntimeError):
         dsk.train_step(m.eval(), opt, xa, xp, xn, label_p, label_n, margin=0.1, epoch=3)
+
+
+@pytest.mark.parametrize("shrink", [1e-2, 1e-4])
+def test_fp16_backward_survives_small_gradients(cuda_dev, shrink):
+    """fp16 activation gradients are multiplied by a static power-of-two loss scale inside the backward
+    (dsk_set_loss_scale, automatic by default).  Late in training the loss - and every gradient with it - is orders of
+    magnitude smaller than in a fresh network: a backward that underflows would stop being linear in the incoming
+    gradient.  Shrinking the loss by 1e-2 / 1e-4 must shrink every parameter gradient by exactly that factor (to fp16
+    rounding), with the automatic scale and, at 1e-4, also with an explicitly raised one."""
+    sd = O.make_state_dict(5, 16)
+    xs = [O.make_input(16, 64, s, 3.0).cuda() for s in (31, 32, 33)]
+
+    def grads_of(mult, scale=None):
+        m = make_model(sd, "fp16", cuda_dev)
+        if scale is not None:
+            m(xs[0])                                      # creates the engine
+            m._engine.set_loss_scale(scale)
+        outs = m.forward_triplet(*xs)
+        loss = dsk.TripletMarginLoss(0.5).forward(*outs) * mult
+        m.zero_grad()
+        loss.backward()
+        return {k: p.grad.detach().double().cpu() / mult for k, p in m.named_parameters() if p.grad is not None}
+
+    ref = grads_of(1.0)
+    small = grads_of(shrink)
+    worst = max((rel_l2(small[k], ref[k]), k) for k in ref)
+    print(f"loss x {shrink:g}: worst gradient rel-L2 vs the unshrunk step {worst[0]:.2e} ({worst[1]})")
+    # 1e-4 with the automatic scale (2^13 at batch 16) puts activation gradients at ~1e-5 * 1e-4 * 8192 ~ 1e-5: fp16
+    # subnormals start at 6e-5 -> a visible but bounded loss; the raised scale below restores full precision
+    assert worst[0] < (2e-3 if shrink >= 1e-2 else 0.25), worst
+    if shrink < 1e-3:
+        raised = grads_of(shrink, scale=2.0 ** 24)
+        worst2 = max((rel_l2(raised[k], ref[k]), k) for k in ref)
+        print(f"  with loss scale 2^24: {worst2[0]:.2e} ({worst2[1]})")
+        assert worst2[0] < 2e-3, worst2
