@@ -36,30 +36,48 @@ __global__ void pack_conv1_umma_kernel(const float* __restrict__ w, uint16_t* __
   }
 }
 
-// x (B, T, 64) fp32; out: zero-padded NHWC 16-bit activation (rows n*(T/2+1)+h+1, 33 pixels per row, 64 channels).
-// grid = B * (T/2) / 4 tiles of 4 output rows x 32 pixels; T/2 must be a multiple of 4.
+// x (B, T, 64) fp32 through tmX: 3-D tensor map (64 bins, T frames, B utterances), box {64, 11, 1}, no swizzle - the 11
+// input rows an output-row quad needs arrive as ONE TMA box; rows above / below the utterance are the map's
+// out-of-bounds zero fill (the conv's zero padding in time), the two padding columns per side are predicated reads.
+// out: zero-padded NHWC 16-bit activation (rows n*(T/2+1)+h+1, 33 pixels per row, 64 channels).
+// Tiles: 4 output rows x 32 pixels; n_tiles = B * (T/2) / 4 (T/2 must be a multiple of 4).
+//
+// Persistent, software-pipelined over the CTA's tiles t_0, t_1, ... (tile = blockIdx.x + k * gridDim.x):
+//     iteration i :  wait patch(t_i)  ->  build A[i&1]  ->  prefetch patch(t_{i+2})  ->  issue MMA(t_i)  ->  epilogue(t_{i-1})
+// so the tensor core works on tile i while the threads write tile i-1 out, and the fbank rows of tile i+2 are in
+// flight.  The weight image, the TMEM allocation (2 x 64 columns) and the barriers are set up once per CTA instead of
+// once per tile (round 1: one tile per CTA, 1280 CTAs, 16 KB of weights re-read by each).
+constexpr int kConv1Threads = 128;
+constexpr int kConv1PatchRows = 11;
+constexpr int kConv1SmemBytes = 2 * 128 * 128 /*A*/ + 2 * 64 * 128 /*B*/ + 2 * kConv1PatchRows * 64 * 4 /*patch*/ + 1024 /*align*/;
+
 template <bool BF16>
-__global__ void __launch_bounds__(128)
-conv1_umma_kernel(const float* __restrict__ x, const uint4* __restrict__ wimg, const float* __restrict__ scale,
-                  const float* __restrict__ bias, uint16_t* __restrict__ out, int T, float clip_hi) {
-  constexpr int WIN = 64, WOUT = 32, ROWS = 4, PATCH_ROWS = 2 * ROWS + 3, PATCH_W = WIN + 4;
-  __shared__ __align__(1024) uint8_t sA[128 * 128];
-  __shared__ __align__(1024) uint8_t sB[2 * 64 * 128];
-  __shared__ float patch[PATCH_ROWS][PATCH_W];
+__global__ void __launch_bounds__(kConv1Threads)
+conv1_umma_kernel(const __grid_constant__ CUtensorMap tmX, const uint4* __restrict__ wimg, const float* __restrict__ scale,
+                  const float* __restrict__ bias, uint16_t* __restrict__ out, int T, int n_tiles, float clip_hi) {
+  constexpr int WOUT = 32, ROWS = 4, PR = kConv1PatchRows;
+  extern __shared__ uint8_t c1_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(c1_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                   // [2][128 rows x 128 B], SWIZZLE_128B K-major
+  uint8_t* sB = sA + 2 * 128 * 128;                     // B1 | B2
+  float* patch = reinterpret_cast<float*>(sB + 2 * 64 * 128);   // [2][11][64]
   __shared__ float s_scale[64], s_bias[64];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t patch_full[2], mma_done[2];
   __shared__ uint32_t tmem_ptr;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int hout = T / 2, tiles_h = hout / ROWS;
-  const int n = blockIdx.x / tiles_h, h0 = (blockIdx.x % tiles_h) * ROWS;
   pdl_launch_dependents();
   if (warp == 0) {
-    tmem_alloc(&tmem_ptr, 64);
+    tmem_alloc(&tmem_ptr, 128);
     tmem_relinquish();
   }
   if (tid == 32) {
-    mbar_init(&bar, 1);
+    tma_prefetch_desc(&tmX);
+    mbar_init(&patch_full[0], 1);
+    mbar_init(&patch_full[1], 1);
+    mbar_init(&mma_done[0], 1);
+    mbar_init(&mma_done[1], 1);
     fence_barrier_init();
   }
   // parameters are safe to read before the dependency wait; the input batch may come from the preceding kernel of
@@ -70,111 +88,124 @@ conv1_umma_kernel(const float* __restrict__ x, const uint4* __restrict__ wimg, c
     s_scale[tid] = scale[tid];
     s_bias[tid] = bias[tid];
   }
-  pdl_wait();
-  {
-    const float* xin = x + static_cast<long>(n) * T * WIN;
-    constexpr int NEL = PATCH_ROWS * PATCH_W, NIT = (NEL + 127) / 128;
-    float t[NIT];
-#pragma unroll
-    for (int j = 0; j < NIT; ++j) {  // all loads first (independent), then the stores
-      const int i = tid + 128 * j;
-      const int pr = i / PATCH_W, pc = i - pr * PATCH_W;
-      const int ih = 2 * h0 - 2 + pr, iw = pc - 2;
-      t[j] = (i < NEL && ih >= 0 && ih < T && iw >= 0 && iw < WIN) ? xin[ih * WIN + iw] : 0.0f;
-    }
-#pragma unroll
-    for (int j = 0; j < NIT; ++j) {
-      const int i = tid + 128 * j;
-      if (i < NEL) patch[i / PATCH_W][i % PATCH_W] = t[j];
-    }
-  }
+  fence_proxy_async_smem();  // B image: generic-proxy writes -> visible to the tensor core's async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_ptr;
+  pdl_wait();
 
-  // ---- operand build: thread = output pixel (r, ow) of the tile = row tid of A
-  {
-    const int r = tid >> 5, ow = tid & 31;
-    uint32_t hi[16], lo[16];  // 32 halfs each, taps 25..31 are zero
-#pragma unroll
-    for (int q = 0; q < 16; ++q) hi[q] = lo[q] = 0u;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const int tap = i * 5 + j;
-        const float v = patch[2 * r + i][2 * ow + j];
-        const uint16_t h16 = to16<BF16>(v);
-        const uint16_t l16 = to16<BF16>(v - from16<BF16>(h16));
-        hi[tap >> 1] |= static_cast<uint32_t>(h16) << ((tap & 1) * 16);
-        lo[tap >> 1] |= static_cast<uint32_t>(l16) << ((tap & 1) * 16);
-      }
-    }
-    uint8_t* row = sA + tid * 128;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      *reinterpret_cast<uint4*>(row + ((c ^ (tid & 7)) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-      *reinterpret_cast<uint4*>(row + (((c + 4) ^ (tid & 7)) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-    }
+  const int my_tiles = (n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  auto tile_of = [&](int i) { return static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x); };
+  auto load_patch = [&](int i) {  // one thread: the 11 x 64 fp32 rows of tile t_i, zero-filled outside the utterance
+    const int t = tile_of(i), n = t / tiles_h, h0 = (t - n * tiles_h) * ROWS;
+    const int b = i & 1;
+    mbar_arrive_expect_tx(&patch_full[b], PR * 64 * 4);
+    tma_load_3d(patch + b * PR * 64, &tmX, &patch_full[b], 0, 2 * h0 - 2, n);
+  };
+  if (tid == 0) {
+    if (my_tiles > 0) load_patch(0);
+    if (my_tiles > 1) load_patch(1);
   }
-  fence_proxy_async_smem();  // generic-proxy writes of A (and B) -> visible to the tensor core's async proxy
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
+
+  // epilogue of tile t_i: TMEM lane = pixel; folded BN, clip, 16-bit pack into the (free) A tile of that buffer, then
+  // cooperative stores: 8 lanes write one 128-byte pixel row, so a warp store covers four full lines
+  auto epilogue = [&](int i) {
+    const int b = i & 1;
+    const int t = tile_of(i), n = t / tiles_h, h0 = (t - n * tiles_h) * ROWS;
+    mbar_wait(&mma_done[b], (i >> 1) & 1);
     tc_fence_after();
-    if (elect_one_sync()) {
-      constexpr uint32_t idesc = umma_idesc_f16(128, 64, BF16);
-      const uint64_t da = umma_desc_sw128(smem_u32(sA));
-      const uint64_t db1 = umma_desc_sw128(smem_u32(sB));
-      const uint64_t db2 = umma_desc_sw128(smem_u32(sB + 64 * 128));
+    uint8_t* stage = sA + b * 128 * 128;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16(tmem_base, da + 2 * k, db1 + 2 * k, idesc, k > 0 ? 1u : 0u);
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + b * 64 + half * 32, v);
+      tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 2; ++k) umma_f16(tmem_base, da + 2 * k, db2 + 2 * k, idesc, 1u);
-      umma_commit(&bar);
-    }
-    __syncwarp();
-  }
-  mbar_wait(&bar, 0);
-  tc_fence_after();
-
-  // ---- epilogue: TMEM lane = pixel; folded BN, clip, 16-bit pack into the (now free) A tile, then cooperative
-  // stores: 8 lanes write one 128-byte pixel row, so a warp store covers four full lines (a thread storing its own
-  // row would touch 32 lines per instruction)
+      for (int g = 0; g < 4; ++g) {
+        float f[8];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t v[32];
-    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + half * 32, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = half * 32 + g * 8 + e;
-        f[e] = fminf(fmaxf(fmaf(__uint_as_float(v[g * 8 + e]), s_scale[c], s_bias[c]), 0.0f), clip_hi);
+        for (int e = 0; e < 8; ++e) {
+          const int c = half * 32 + g * 8 + e;
+          f[e] = fminf(fmaxf(fmaf(__uint_as_float(v[g * 8 + e]), s_scale[c], s_bias[c]), 0.0f), clip_hi);
+        }
+        *reinterpret_cast<uint4*>(stage + tid * 128 + (((half * 4 + g) ^ (tid & 7)) << 4)) =
+            make_uint4(pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]), pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
       }
-      *reinterpret_cast<uint4*>(sA + tid * 128 + (((half * 4 + g) ^ (tid & 7)) << 4)) =
-          make_uint4(pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]), pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
     }
-  }
-  __syncthreads();
-  {
+    tc_fence_before();
+    __syncthreads();
     const int chunk = tid & 7;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = i * 16 + (tid >> 3);
-      const uint4 val = *reinterpret_cast<const uint4*>(sA + row * 128 + ((chunk ^ (row & 7)) << 4));
+    for (int k = 0; k < 8; ++k) {
+      const int row = k * 16 + (tid >> 3);
+      const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
       const long pix = (static_cast<long>(n) * (hout + 1) + h0 + (row >> 5) + 1) * (WOUT + 1) + 1 + (row & 31);
       reinterpret_cast<uint4*>(out + pix * 64)[chunk] = val;
     }
+    __syncthreads();  // the staging tile is the next-but-one operand tile: every row has been copied out before it is rebuilt
+  };
+
+  for (int i = 0; i < my_tiles; ++i) {
+    const int b = i & 1;
+    mbar_wait(&patch_full[b], (i >> 1) & 1);
+    // ---- operand build: thread = output pixel (r, ow) of the tile = row tid of A[b]
+    {
+      const float* pt = patch + b * PR * 64;
+      const int r = tid >> 5, ow = tid & 31;
+      uint32_t hi[16], lo[16];  // 32 halfs each, taps 25..31 are zero
+#pragma unroll
+      for (int q = 0; q < 16; ++q) hi[q] = lo[q] = 0u;
+#pragma unroll
+      for (int ii = 0; ii < 5; ++ii) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int tap = ii * 5 + j;
+          const int iw = 2 * ow + j - 2;
+          const float v = (static_cast<unsigned>(iw) < 64u) ? pt[(2 * r + ii) * 64 + iw] : 0.0f;
+          const uint16_t h16 = to16<BF16>(v);
+          const uint16_t l16 = to16<BF16>(v - from16<BF16>(h16));
+          hi[tap >> 1] |= static_cast<uint32_t>(h16) << ((tap & 1) * 16);
+          lo[tap >> 1] |= static_cast<uint32_t>(l16) << ((tap & 1) * 16);
+        }
+      }
+      // A[b] is free: its last reader, the cooperative store of tile i-2's epilogue, ended before the previous
+      // iteration's last __syncthreads
+      uint8_t* row = sA + b * 128 * 128 + tid * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        *reinterpret_cast<uint4*>(row + ((c ^ (tid & 7)) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        *reinterpret_cast<uint4*>(row + (((c + 4) ^ (tid & 7)) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+      }
+    }
+    fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core's async proxy
+    tc_fence_before();
+    __syncthreads();           // A[b] complete; patch[b] consumed by every thread
+    if (tid == 0 && i + 2 < my_tiles) load_patch(i + 2);
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one_sync()) {
+        constexpr uint32_t idesc = umma_idesc_f16(128, 64, BF16);
+        const uint64_t da = umma_desc_sw128(smem_u32(sA + b * 128 * 128));
+        const uint64_t db1 = umma_desc_sw128(smem_u32(sB));
+        const uint64_t db2 = umma_desc_sw128(smem_u32(sB + 64 * 128));
+        const uint32_t d = tmem_base + b * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(d, da + 2 * k, db1 + 2 * k, idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma_f16(d, da + 2 * k, db2 + 2 * k, idesc, 1u);
+        umma_commit(&mma_done[b]);
+      }
+      __syncwarp();
+    }
+    if (i > 0) epilogue(i - 1);  // under MMA(t_i)
   }
+  if (my_tiles > 0) epilogue(my_tiles - 1);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 

@@ -94,7 +94,7 @@ EncodeTiledFn get_encode_fn() {
 // 16-bit tensor map, 128B swizzle, zero OOB fill. dims/strides innermost first; strides[i] is the byte
 // stride of dim i+1.
 int make_tmap(CUtensorMap* out, bool bf16, const void* ptr, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, bool f32 = false) {
+              const uint64_t* strides_bytes, const uint32_t* box, bool f32 = false, bool swizzle128 = true) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(DSK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gd[5];
@@ -109,7 +109,8 @@ int make_tmap(CUtensorMap* out, bool bf16, const void* ptr, int rank, const uint
   }
   CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                            : (bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), rank,
-                  const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     std::string d;
@@ -1181,6 +1182,21 @@ void adopt_shared_weights(dsk_handle h) {
   h->seen_epoch = s->weights_epoch;
 }
 
+// conv1: tensor map over the input batch (64 bins, T frames, B utterances; box = the 11 frames x 64 bins of one tile,
+// out-of-bounds rows zero) and the persistent grid (<= 4 CTAs per SM, the same number of tiles for every CTA)
+int conv1_launch_geometry(const dsk_handle_s* h, const float* x, int B, int T, CUtensorMap* tm, int* grid, int* n_tiles) {
+  const uint64_t dims[3] = {64, static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+  const uint64_t strides[2] = {64 * sizeof(float), static_cast<uint64_t>(T) * 64 * sizeof(float)};
+  const uint32_t box[3] = {64, static_cast<uint32_t>(dsk::kConv1PatchRows), 1};
+  int rc = make_tmap(tm, false, x, 3, dims, strides, box, /*f32=*/true, /*swizzle128=*/false);
+  if (rc) return rc;
+  const int nt = B * (T / 2 / 4);
+  const int per_cta = (nt + 4 * h->num_sms - 1) / (4 * h->num_sms);
+  *n_tiles = nt;
+  *grid = (nt + per_cta - 1) / per_cta;
+  return DSK_OK;
+}
+
 // the 15 launches of one eval forward on stream s
 int enqueue_forward(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B, int T, float* emb, cudaStream_t s) {
   int rc = 0;
@@ -1197,15 +1213,21 @@ int enqueue_forward(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B,
     cudaEventRecord(h->events[h->n_marks++], s);
   };
   mark(true);
-  // conv1 (+bn1 +clip)
+  // conv1 (+bn1 +clip): persistent CTAs, the fbank rows of each tile staged by TMA
   {
-    const int blocks = B * (T / 2 / 4);  // 4 output rows x 32 pixels per CTA
-    if (h->bf16)
-      CUDA_TRY(launch_opt(h->conv1_pdl, dsk::conv1_umma_kernel<true>, dim3(blocks), dim3(128), 0, s, x, (const uint4*)h->conv1_img,
-                          (const float*)h->scale[0], (const float*)h->bias[0], (uint16_t*)pl->act[0], T, 20.0f));
-    else
-      CUDA_TRY(launch_opt(h->conv1_pdl, dsk::conv1_umma_kernel<false>, dim3(blocks), dim3(128), 0, s, x, (const uint4*)h->conv1_img,
-                          (const float*)h->scale[0], (const float*)h->bias[0], (uint16_t*)pl->act[0], T, 20.0f));
+    CUtensorMap tmX;
+    int grid = 0, n_tiles = 0;
+    rc = conv1_launch_geometry(h, x, B, T, &tmX, &grid, &n_tiles);
+    if (rc) return rc;
+    if (h->bf16) {
+      if (int rc2 = ensure_smem_optin(reinterpret_cast<const void*>(dsk::conv1_umma_kernel<true>), dsk::kConv1SmemBytes)) return rc2;
+      CUDA_TRY(launch_opt(h->conv1_pdl, dsk::conv1_umma_kernel<true>, dim3(grid), dim3(dsk::kConv1Threads), dsk::kConv1SmemBytes, s, tmX,
+                          (const uint4*)h->conv1_img, (const float*)h->scale[0], (const float*)h->bias[0], (uint16_t*)pl->act[0], T, n_tiles, 20.0f));
+    } else {
+      if (int rc2 = ensure_smem_optin(reinterpret_cast<const void*>(dsk::conv1_umma_kernel<false>), dsk::kConv1SmemBytes)) return rc2;
+      CUDA_TRY(launch_opt(h->conv1_pdl, dsk::conv1_umma_kernel<false>, dim3(grid), dim3(dsk::kConv1Threads), dsk::kConv1SmemBytes, s, tmX,
+                          (const uint4*)h->conv1_img, (const float*)h->scale[0], (const float*)h->bias[0], (uint16_t*)pl->act[0], T, n_tiles, 20.0f));
+    }
     mark(true);
   }
   for (int i = 1; i < DSK_NUM_CONV; ++i) {
@@ -1239,8 +1261,11 @@ int enqueue_forward(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B,
 void conv1_node_params(dsk_handle h, dsk_handle_s::Plan* pl, int B, int T, cudaKernelNodeParams* kp) {
   memset(kp, 0, sizeof(*kp));
   kp->func = h->bf16 ? reinterpret_cast<void*>(dsk::conv1_umma_kernel<true>) : reinterpret_cast<void*>(dsk::conv1_umma_kernel<false>);
-  kp->gridDim = dim3(B * (T / 2 / 4));
-  kp->blockDim = dim3(128);
+  const int nt = B * (T / 2 / 4);
+  const int per_cta = (nt + 4 * h->num_sms - 1) / (4 * h->num_sms);
+  kp->gridDim = dim3((nt + per_cta - 1) / per_cta);
+  kp->blockDim = dim3(dsk::kConv1Threads);
+  kp->sharedMemBytes = dsk::kConv1SmemBytes;
 }
 
 // Capture the forward into a graph (stream capture keeps the programmatic-launch edges).  Any failure just leaves the
@@ -1298,12 +1323,16 @@ int retarget_forward_graph(dsk_handle h, dsk_handle_s::Plan* pl, const float* x,
   if (x != pl->g_x) {
     cudaKernelNodeParams kp;
     conv1_node_params(h, pl, B, T, &kp);
+    alignas(64) CUtensorMap tmX;   // the input pointer lives inside the tensor map: re-encode it for this batch
+    int grid = 0, n_tiles = 0;
+    int rc = conv1_launch_geometry(h, x, B, T, &tmX, &grid, &n_tiles);
+    if (rc) return rc;
     const uint4* wimg = reinterpret_cast<const uint4*>(h->conv1_img);
     const float *sc = h->scale[0], *bi = h->bias[0];
     uint16_t* out = static_cast<uint16_t*>(pl->act[0]);
     int Tv = T;
     float clip = 20.0f;
-    void* args[7] = {&x, &wimg, &sc, &bi, &out, &Tv, &clip};
+    void* args[8] = {&tmX, &wimg, &sc, &bi, &out, &Tv, &n_tiles, &clip};
     kp.kernelParams = args;
     CUDA_TRY(cudaGraphExecKernelNodeSetParams(pl->gexec, pl->node_first, &kp));
     pl->g_x = x;
