@@ -282,6 +282,7 @@ struct dsk_train_ctx_s {
   float *pooled = nullptr, *fc_out = nullptr, *fc_part = nullptr, *inv_norm = nullptr;
   float *scale_t = nullptr, *shift_t = nullptr, *partial = nullptr, *coef = nullptr;
   float *g_fc = nullptr, *dP = nullptr, *dwacc = nullptr, *c1part = nullptr;
+  float* ls = nullptr;                 // {S, 1/S}: this backward's loss scale, chosen on the device (loss_scale_kernel)
   void *gA = nullptr, *gB = nullptr, *G = nullptr, *gres = nullptr;
   ConvLaunch conv[DSK_NUM_CONV];       // forward convs 1..11 (raw output, no epilogue math)
   ConvLaunch dgrad[DSK_NUM_CONV][4];
@@ -291,7 +292,8 @@ struct dsk_train_ctx_s {
 
 namespace {
 
-constexpr int kStatBlocksMax = 1200;
+constexpr int kStatBlocksMax = 592;  // partial rows per 64-channel group of the BatchNorm reductions (4 blocks per SM: the
+                                     // single-block finalize kernels walk these rows, ~8 us each at 1200)
 // K-split count of the weight-gradient GEMM of a layer (>= 2 work items per SM), before the per-batch cap
 int wgrad_ksplit_bound(int num_sms, int cout, int cin, int taps) {
   const bool swapped = cout == 64;
@@ -1450,7 +1452,7 @@ static int ctx_create(dsk_handle h, int cap, int T, cudaStream_t s, dsk_train_ct
   }
   const size_t o_pooled = take(static_cast<size_t>(B) * 2048 * 4), o_fc = take(static_cast<size_t>(B) * h->emb * 4);
   const size_t o_fc_part = take(static_cast<size_t>(dsk::kFcSplit) * B * h->emb * 4);
-  const size_t o_inv = take(B * 4), o_sc = take(512 * 4), o_sh = take(512 * 4);
+  const size_t o_inv = take(B * 4), o_sc = take(512 * 4), o_sh = take(512 * 4), o_ls = take(2 * 4);
   const size_t o_part = take(static_cast<size_t>(kStatBlocksMax) * 2 * 512 * 4), o_coef = take(3 * 512 * 4);
   const size_t o_gfc = take(static_cast<size_t>(B) * h->emb * 4), o_dP = take(static_cast<size_t>(B) * 2048 * 4);
   size_t dw_bytes = 0;  // [ksplit][tap][cout][cin] fp32 slices of the largest layer
@@ -1483,6 +1485,7 @@ static int ctx_create(dsk_handle h, int cap, int T, cudaStream_t s, dsk_train_ct
   c->inv_norm = reinterpret_cast<float*>(b + o_inv);
   c->scale_t = reinterpret_cast<float*>(b + o_sc);
   c->shift_t = reinterpret_cast<float*>(b + o_sh);
+  c->ls = reinterpret_cast<float*>(b + o_ls);
   c->partial = reinterpret_cast<float*>(b + o_part);
   c->coef = reinterpret_cast<float*>(b + o_coef);
   c->g_fc = reinterpret_cast<float*>(b + o_gfc);
@@ -1562,17 +1565,6 @@ int32_t dsk_set_loss_scale(dsk_handle h, float scale) {
   if (scale < 0.f) return fail(DSK_ERR_INVALID, "loss scale must be >= 0 (0 = automatic)");
   h->loss_scale = scale;
   return DSK_OK;
-}
-
-static float effective_loss_scale(const dsk_handle_s* h, int B) {
-  if (h->loss_scale > 0.f) return h->loss_scale;
-  if (h->bf16) return 1.0f;
-  // fp16 gradients: activations' gradients scale like 1/B (mean over the batch); keep them near 2^-4 .. 2^4
-  int lg = 0;
-  while ((1 << (lg + 1)) <= B) ++lg;
-  int e = 9 + lg;
-  if (e > 16) e = 16;
-  return static_cast<float>(1 << e);
 }
 
 int32_t dsk_rescnn_forward_train(dsk_handle h, const float* x, int32_t B, int32_t T, float* emb, dsk_train_ctx* ctx_out,
@@ -1677,10 +1669,12 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool bf = h->bf16;
   const int B = c->B, T = c->T, E = h->emb;
-  const float S = effective_loss_scale(h, B);
-  const float invS = 1.0f / S;
   // tail
   dsk::l2norm_bwd_kernel<<<B, 128, 0, s>>>(c->fc_out, c->inv_norm, grad_emb, c->g_fc, E, 10.0f);
+  KERNEL_CHECK();
+  // the loss scale of this backward: explicit (dsk_set_loss_scale), 1 for bf16 operands, else chosen on the device
+  dsk::loss_scale_kernel<<<1, 1024, 0, s>>>(c->g_fc, static_cast<long>(B) * E, h->loss_scale > 0.f ? h->loss_scale : (bf ? 1.0f : 0.0f),
+                                            c->ls);
   KERNEL_CHECK();
   dsk::fc_bwd_weight_kernel<<<dim3(E / 8, 2048 / 256), 256, 0, s>>>(c->g_fc, c->pooled, g->fc_w, g->fc_b, B, 2048, E, 512, 4);
   KERNEL_CHECK();
@@ -1688,8 +1682,8 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
   KERNEL_CHECK();
   {
     const int H4 = T / 16;
-    if (bf) dsk::pool_bwd_kernel<true><<<B, 256, 0, s>>>(c->dP, (uint16_t*)c->gA, H4, 2048, S / H4);
-    else dsk::pool_bwd_kernel<false><<<B, 256, 0, s>>>(c->dP, (uint16_t*)c->gA, H4, 2048, S / H4);
+    if (bf) dsk::pool_bwd_kernel<true><<<B, 256, 0, s>>>(c->dP, (uint16_t*)c->gA, H4, 2048, 1.0f / H4, c->ls);
+    else dsk::pool_bwd_kernel<false><<<B, 256, 0, s>>>(c->dP, (uint16_t*)c->gA, H4, 2048, 1.0f / H4, c->ls);
     KERNEL_CHECK();
   }
   for (int i = DSK_NUM_CONV - 1; i >= 0; --i) {
@@ -1706,8 +1700,8 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
       dsk::bn_bwd_reduce_kernel<false><<<gs, 256, 0, s>>>(gy, (const uint16_t*)c->y[i], c->raw[i], c->mean[i],
                                                           c->rstd[i], M, C, 20.0f, c->partial);
     KERNEL_CHECK();
-    dsk::bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], c->rstd[i], invS,
-                                                               g->bn_gamma[i], g->bn_beta[i], c->coef);
+    dsk::bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(c->partial, gx, C, M, h->w.bn_gamma[i], c->rstd[i], 1.0f,
+                                                               g->bn_gamma[i], g->bn_beta[i], c->coef, c->ls);
     KERNEL_CHECK();
     uint16_t* gres = (i % 3 == 2) ? (uint16_t*)c->gres : nullptr;
     dim3 ga(static_cast<unsigned>((M + 63) / 64), C / 64);
@@ -1724,7 +1718,7 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
       if (bf) dsk::conv1_wgrad_partial_kernel<true><<<nblk, 256, 0, s>>>((const uint16_t*)c->G, c->x, B, T, c->c1part);
       else dsk::conv1_wgrad_partial_kernel<false><<<nblk, 256, 0, s>>>((const uint16_t*)c->G, c->x, B, T, c->c1part);
       KERNEL_CHECK();
-      dsk::sum_partials_kernel<<<(1600 + 31) / 32, 1024, 0, s>>>(c->c1part, nblk, 1600, invS, g->conv_w[0]);
+      dsk::sum_partials_kernel<<<(1600 + 31) / 32, 1024, 0, s>>>(c->c1part, nblk, 1600, 1.0f, g->conv_w[0], c->ls);
       KERNEL_CHECK();
     } else {
       const int taps = lc.ksize * lc.ksize;
@@ -1732,7 +1726,7 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx c, const float* grad_emb
       rc = launch_wgrad(h, c->wgrad[i], s);
       if (rc) return rc;
       dsk::unpack_wgrad_kernel<<<static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, s>>>(
-          c->dwacc, g->conv_w[i], lc.cout, lc.cin, taps, invS, c->wgrad[i].p.ksplit, c->wgrad[i].p.slice_elems);
+          c->dwacc, g->conv_w[i], lc.cout, lc.cin, taps, 1.0f, c->wgrad[i].p.ksplit, c->wgrad[i].p.slice_elems, c->ls);
       KERNEL_CHECK();
       for (int k = 0; k < c->n_dgrad[i]; ++k) {
         rc = launch_conv(h, c->dgrad[i][k], s);

@@ -297,10 +297,11 @@ bn_bwd_reduce_kernel(const uint16_t* __restrict__ gy, const uint16_t* __restrict
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long M,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
                                        float inv_loss_scale, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ coef /*[3][C]*/) {
+                                       float* __restrict__ coef /*[3][C]*/, const float* __restrict__ dyn = nullptr) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s, ss;
   if (!bn_partial_totals(partial, nblk, C, c, s, ss)) return;
+  if (dyn) inv_loss_scale *= dyn[1];  // device-side loss scale of this backward: {S, 1/S}
   dbeta[c] = static_cast<float>(s) * inv_loss_scale;
   dgamma[c] = static_cast<float>(ss) * inv_loss_scale;
   coef[c] = gamma[c] * rstd[c];
@@ -408,8 +409,10 @@ fc_bwd_input_kernel(const float* __restrict__ gy, const float* __restrict__ wq, 
 
 // g_y[b][h][w][c] = loss_scale * dP[b][w*C + c] / H  (mean over time backward) -> 16-bit NHWC
 template <bool BF16>
-__global__ void pool_bwd_kernel(const float* __restrict__ dP, uint16_t* __restrict__ gy, int H, int WC, float mult) {
+__global__ void pool_bwd_kernel(const float* __restrict__ dP, uint16_t* __restrict__ gy, int H, int WC, float mult,
+                                const float* __restrict__ dyn = nullptr) {
   const int b = blockIdx.x;
+  if (dyn) mult *= dyn[0];  // device-side loss scale of this backward: {S, 1/S}
   for (int i = threadIdx.x; i < WC; i += blockDim.x) {
     const uint16_t v = to16<BF16>(dP[static_cast<long>(b) * WC + i] * mult);
     for (int h = 0; h < H; ++h) gy[(static_cast<long>(b) * H + h) * WC + i] = v;
@@ -496,8 +499,9 @@ conv1_wgrad_partial_kernel(const uint16_t* __restrict__ G, const float* __restri
 // out[i] = mult * sum_b partial[b][i].  grid ceil(n/32), block 1024: thread (slice, i) adds every 32nd row in double,
 // slices are combined in fixed order.
 __global__ void sum_partials_kernel(const float* __restrict__ partial, int nblk, int n, float mult,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, const float* __restrict__ dyn = nullptr) {
   __shared__ double red[32][33];
+  if (dyn) mult *= dyn[1];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   double t = 0.0;
@@ -523,8 +527,9 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int nblk,
 // K-split partial weight gradients fp32 [ksplit][tap][co][ci] (one slice per split of the wgrad GEMM) -> OIHW
 // [co][ci][tap], slices added in fixed order (deterministic), scaled by mult.  Reads are coalesced along ci.
 __global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restrict__ out, int cout, int cin, int taps,
-                                    float mult, int ksplit, long slice_elems) {
+                                    float mult, int ksplit, long slice_elems, const float* __restrict__ dyn = nullptr) {
   const long total = static_cast<long>(cout) * cin * taps;
+  if (dyn) mult *= dyn[1];
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int ci = i % cin;
@@ -534,6 +539,34 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ in, float* __restr
     float acc = in[i];
     for (int k = 1; k < ksplit; ++k) acc += in[k * slice_elems + i];
     out[(static_cast<long>(co) * cin + ci) * taps + tap] = acc * mult;
+  }
+}
+
+// Loss scale of ONE backward, chosen on the device (no host round trip): 16-bit gradient tensors are multiplied by a
+// power of two S inside the backward and every parameter gradient is divided by it again.  S puts the largest incoming
+// gradient max|dL/d(fc output)| at ~2^9 - the operating point of round 1's static rule 2^(9 + log2 B) on a fresh network,
+// but following the loss as it shrinks during training (a static scale lets late-training gradients sink into fp16
+// subnormals: tests/test_gpu_train.py::test_fp16_backward_survives_small_gradients).  fixed > 0 overrides (bf16: 1).
+// ls = {S, 1/S}.  grid 1, block 1024.
+__global__ void loss_scale_kernel(const float* __restrict__ g, long n, float fixed, float* __restrict__ ls) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(g[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < static_cast<int>(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+    float S = fixed;
+    if (!(S > 0.f)) {
+      S = 1.f;
+      if (m > 0.f && isfinite(m)) {
+        S = exp2f(floorf(log2f(512.f / m)));
+        S = fminf(fmaxf(S, 5.9604645e-8f /*2^-24*/), 1.0995116e12f /*2^40*/);
+      }
+    }
+    ls[0] = S;
+    ls[1] = 1.f / S;
   }
 }
 

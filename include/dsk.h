@@ -123,8 +123,10 @@ int32_t dsk_rescnn_backward(dsk_handle h, dsk_train_ctx ctx, const float* grad_e
 int32_t dsk_train_ctx_read(dsk_handle h, dsk_train_ctx ctx, int32_t which, int32_t layer, float* out_nchw, void* stream);
 /* Return an unused context to the pool (forward without backward, e.g. under no_grad). */
 int32_t dsk_train_ctx_release(dsk_handle h, dsk_train_ctx ctx);
-/* fp16 operands: gradients of activations are multiplied by this power of two inside the backward and divided
- * out of every parameter gradient (0 = automatic: 2^(9+floor(log2 B)) capped at 2^16 for fp16, 1 for bf16). */
+/* fp16 operands: inside the backward the 16-bit gradient tensors are multiplied by a power of two S and every parameter
+ * gradient is divided by it again.  scale = 0 (default): S is chosen PER BACKWARD ON THE DEVICE from the largest incoming
+ * gradient, S = 2^floor(log2(512 / max|dL/d(fc output)|)) - no host synchronisation, follows the loss as it shrinks during
+ * training; scale > 0: that fixed value.  bf16 operands: 1 unless set. */
 int32_t dsk_set_loss_scale(dsk_handle h, float scale);
 
 /* Device timing of the next dsk_rescnn_forward calls (which then launch kernel by kernel, not as a graph).
