@@ -698,8 +698,9 @@ def main():
         return
 
     # the data-parallel allreduce rides NVLink only (north star): no InfiniBand / socket transport on the one box
+    # (NCCL_P2P_LEVEL is left to NCCL: forcing "NVL" made it drop to shared-memory transport on a 2-GPU lease whose
+    #  topology it does not report as NVLink - 9.25 ms instead of 7.4 ms per training step)
     os.environ.setdefault("NCCL_IB_DISABLE", "1")
-    os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
     import torch
     import torch.distributed as dist
 

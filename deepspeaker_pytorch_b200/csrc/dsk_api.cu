@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -16,6 +17,7 @@
 #include "conv_umma.cuh"
 #include "conv3x3_halo.cuh"
 #include "conv1_umma.cuh"
+#include "fbank_kernels.cuh"
 #include "head_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "metric_kernels.cuh"
@@ -1274,6 +1276,8 @@ void conv1_node_params(dsk_handle h, dsk_handle_s::Plan* pl, int B, int T, cudaK
 // plan on the kernel-by-kernel path.
 void build_forward_graph(dsk_handle h, dsk_handle_s::Plan* pl, const float* x, int B, int T, float* emb, cudaStream_t s) {
   pl->graph_failed = true;  // until proven otherwise
+  // the legacy default stream cannot be captured: forwards issued on it stay on the kernel-by-kernel path
+  if (s == nullptr || s == cudaStreamLegacy) return;
   if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
     cudaGetLastError();
     return;
@@ -2422,6 +2426,61 @@ int32_t dsk_pipeline_sync(dsk_pipeline p) {
 int32_t dsk_pipeline_lane_stream(dsk_pipeline p, int32_t lane, void** stream_out) {
   if (!p || lane < -2 || lane >= p->lanes || !stream_out) return fail(DSK_ERR_INVALID, "dsk_pipeline_lane_stream: bad arguments");
   *stream_out = lane == -1 ? p->h2d : lane == -2 ? p->d2h : p->lane_stream[lane];
+  return DSK_OK;
+}
+
+
+// ---- log-fbank front-end (audio_processing.py:9-36) ------------------------------------------------------------------
+static long fbank_round_half_up(double v) { return static_cast<long>(std::floor(v + 0.5)); }
+
+int64_t dsk_fbank_num_frames(int64_t n_samples, int32_t sample_rate) {
+  if (n_samples <= 0 || sample_rate <= 0) return 0;
+  const long flen = fbank_round_half_up(0.025 * sample_rate), step = fbank_round_half_up(0.01 * sample_rate);
+  if (n_samples <= flen) return 1;
+  return 1 + static_cast<int64_t>(std::ceil((static_cast<double>(n_samples) - flen) / step));
+}
+
+int32_t dsk_fbank(const float* audio, int64_t n_samples, int32_t sample_rate, int32_t log_scale, int32_t subtract_mean,
+                  float* feat, void* stream) {
+  if (!audio || !feat || n_samples <= 0 || n_samples >= (1ll << 31) || sample_rate <= 0)
+    return fail(DSK_ERR_INVALID, "dsk_fbank: bad arguments");
+  const long flen = fbank_round_half_up(0.025 * sample_rate), step = fbank_round_half_up(0.01 * sample_rate);
+  if (flen > dsk::kFbNfft) return fail(DSK_ERR_INVALID, "dsk_fbank: the 25 ms frame (%ld samples) exceeds NFFT = 512", flen);
+  const int frames = static_cast<int>(dsk_fbank_num_frames(n_samples, sample_rate));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // python_speech_features.get_filterbanks(nfilt=64, nfft=512, samplerate, lowfreq=0, highfreq=samplerate/2)
+  std::vector<float> fb(static_cast<size_t>(dsk::kFbFilters) * dsk::kFbBins, 0.f);
+  {
+    auto hz2mel = [](double hz) { return 2595.0 * std::log10(1.0 + hz / 700.0); };
+    auto mel2hz = [](double mel) { return 700.0 * (std::pow(10.0, mel / 2595.0) - 1.0); };
+    const double lowmel = hz2mel(0.0), highmel = hz2mel(sample_rate / 2.0);
+    double bin[dsk::kFbFilters + 2];
+    for (int i = 0; i < dsk::kFbFilters + 2; ++i) {
+      const double mel = lowmel + (highmel - lowmel) * i / (dsk::kFbFilters + 1);
+      bin[i] = std::floor((dsk::kFbNfft + 1) * mel2hz(mel) / sample_rate);
+    }
+    for (int j = 0; j < dsk::kFbFilters; ++j) {
+      for (int i = static_cast<int>(bin[j]); i < static_cast<int>(bin[j + 1]); ++i)
+        fb[j * dsk::kFbBins + i] = static_cast<float>((i - bin[j]) / (bin[j + 1] - bin[j]));
+      for (int i = static_cast<int>(bin[j + 1]); i < static_cast<int>(bin[j + 2]); ++i)
+        fb[j * dsk::kFbBins + i] = static_cast<float>((bin[j + 2] - i) / (bin[j + 2] - bin[j + 1]));
+    }
+  }
+  const int nblk = (frames + dsk::kFbFramesPerBlock - 1) / dsk::kFbFramesPerBlock;
+  float* scratch = nullptr;  // [64][257] filterbank + [nblk][64] column-sum partials
+  const size_t fb_bytes = fb.size() * sizeof(float);
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), fb_bytes + static_cast<size_t>(nblk) * dsk::kFbFilters * sizeof(float), s));
+  CUDA_TRY(cudaMemcpyAsync(scratch, fb.data(), fb_bytes, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // fb is a stack-lifetime host vector (pageable copy): front-end call, not the hot loop
+  float* partial = scratch + fb.size();
+  dsk::fbank_kernel<<<nblk, dsk::kFbThreads, 0, s>>>(audio, static_cast<int>(n_samples), static_cast<int>(flen), static_cast<int>(step),
+                                                      frames, 0.97f, scratch, log_scale, 1e-5f, feat, partial);
+  KERNEL_CHECK();
+  if (subtract_mean) {
+    dsk::fbank_mean_sub_kernel<<<(frames + 63) / 64, 256, 0, s>>>(feat, frames, partial, nblk);
+    KERNEL_CHECK();
+  }
+  CUDA_TRY(cudaFreeAsync(scratch, s));
   return DSK_OK;
 }
 

@@ -268,6 +268,17 @@ int32_t dsk_pipeline_wait(dsk_pipeline p, int64_t ticket);
 int32_t dsk_pipeline_sync(dsk_pipeline p);
 int32_t dsk_pipeline_lane_stream(dsk_pipeline p, int32_t lane, void** stream_out);
 
+/* Log mel-filterbank front-end of the reference (/root/reference/audio_processing.py:9-36 mk_MFB with constants.py:
+ * python_speech_features.fbank(audio, samplerate, nfilt=64, winlen=0.025) -> 20*log10(max(., 1e-5)) (log_scale) -> minus the
+ * per-bin mean over the utterance (subtract_mean, normalize_frames with Scale=False).  audio: n_samples fp32 mono on the
+ * device; feat: (dsk_fbank_num_frames(n_samples, sample_rate), 64) fp32 row-major, the (T, 64) layout the network's input
+ * is cropped from.  python_speech_features is not vendored in the reference (parity against it unpinned): its published
+ * algorithm is restated (pre-emphasis 0.97, 25 ms / 10 ms rectangular frames, NFFT 512, |rfft|^2 / NFFT, triangular mel
+ * filters, zeros -> eps). */
+int64_t dsk_fbank_num_frames(int64_t n_samples, int32_t sample_rate);
+int32_t dsk_fbank(const float* audio, int64_t n_samples, int32_t sample_rate, int32_t log_scale, int32_t subtract_mean,
+                  float* feat, void* stream);
+
 /* Threshold sweep of the verification metric (/root/reference/eval_metrics.py:16-37 calculate_roc, :53-88 calculate_val /
  * calculate_val_far; called from train_triplet.py:361): for every threshold t (double, as numpy's arange yields them)
  * tp[t] = #{i : same[i] && (double)dist[i] < t}, fp[t] = #{i : !same[i] && (double)dist[i] < t} — numpy's

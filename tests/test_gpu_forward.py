@@ -124,29 +124,49 @@ def test_graph_launch_equals_kernel_by_kernel(models):
     sd, _ = models
     mg = _fresh_model(sd, {"DSK_GRAPH": "1"})
     mp = _fresh_model(sd, {"DSK_GRAPH": "0"})
+    side = torch.cuda.Stream()      # the legacy default stream cannot be captured: the graph path needs a real stream
+    cur = torch.cuda.current_stream()
+
+    def graph_forward(x):
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out = mg(x)
+        cur.wait_stream(side)
+        return out
+
     with torch.no_grad():
         for i in range(4):                      # call 0 plain (warm-up), call 1 captures, calls 2-3 re-target
             x = O.make_input(5, 48, seed=40 + i, scale=4.0).cuda()
-            a = mg(x)
+            a = graph_forward(x)
             b = mp(x)
             assert torch.equal(a, b), i
         x = O.make_input(3, 32, seed=50, scale=4.0).cuda()   # a new shape drops the plan and its graph
-        assert torch.equal(mg(x), mp(x))
+        assert torch.equal(graph_forward(x), mp(x))
         x = O.make_input(5, 48, seed=51, scale=4.0).cuda()
-        assert torch.equal(mg(x), mp(x))
+        assert torch.equal(graph_forward(x), mp(x))
 
 
 def test_graph_follows_weight_reload(models):
     sd, _ = models
-    m = _fresh_model(sd, {"DSK_GRAPH": "1"})
+    mm = _fresh_model(sd, {"DSK_GRAPH": "1"})
+    side, cur = torch.cuda.Stream(), torch.cuda.current_stream()
+
+    def m(x):                                   # on a capturable stream (see test_graph_launch_equals_kernel_by_kernel)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out = mm(x)
+        cur.wait_stream(side)
+        return out
+
     x = O.make_input(4, 32, seed=60, scale=3.0).cuda()
     with torch.no_grad():
         for _ in range(3):
             e0 = m(x)
-        m.model.fc.bias.add_(0.25)              # bumps the parameter version -> weights reloaded, plans rebuilt
+        mm.model.fc.bias.add_(0.25)             # bumps the parameter version -> weights reloaded, plans rebuilt
+        cur.synchronize()
         e1 = m(x)
         e2 = m(x)
-        ref = O.forward({k: v.cpu() for k, v in m.state_dict().items()}, x.cpu())
+        ref = O.forward({k: v.cpu() for k, v in mm.state_dict().items()}, x.cpu())
     assert not torch.equal(e0, e1)
     assert torch.equal(e1, e2)
     assert ((e1.cpu() - ref).norm(dim=1) / ref.norm(dim=1)).max().item() < 1e-3

@@ -108,15 +108,15 @@ def test_gradients_are_bit_reproducible(cuda_dev):
 
 
 def test_adagrad_loss_trajectory_follows_the_oracle(cuda_dev):
-    """20 branch-A steps with the fused Adagrad (train_triplet.py:215-224 + :369-383) against the oracle stepped by
+    """12 branch-A steps with the fused Adagrad (train_triplet.py:215-224 + :369-383) against the oracle stepped by
     torch.optim.Adagrad on the CPU, on ONE fixed triplet batch (an overfitting run).
 
-    Why a fixed batch: Adagrad's first steps move every weight by lr * g / |g| = +-lr whatever the gradient's size, so
-    the elements whose gradient is rounding noise move in random directions; with a fresh batch per step the loss
-    sequence is dominated by that noise after two steps (measured: 7 % at step 3, 36 % by step 6 against the fp32
-    oracle, with the first two steps agreeing to 1e-3).  On a fixed batch the loss is driven by the consistent part of
-    the gradient: both implementations must drive it down at the same rate."""
-    B, T, steps, lr = 8, 64, 20, 1e-3
+    Adagrad's first steps move every weight by lr * g / |g| = +-lr whatever the gradient's size.  With a fresh batch per
+    step the loss sequence is rounding noise after two steps (7 % at step 3, 36 % by step 6 against the fp32 oracle, the
+    first two steps agreeing to 1e-3), and on a fixed batch any lr >= 2e-5 drives the hinge to exactly zero in ONE step
+    (both implementations: uninformative).  lr = 1e-6 gives the oracle a smooth descent 0.63 -> 0.18 over 12 steps, which
+    the engine has to follow step by step."""
+    B, T, steps, lr = 8, 32, 12, 1e-6
     sd = O.make_state_dict(3, 16)
     m = make_model(sd, "fp16", cuda_dev)
     opt = dsk.FusedAdagrad(m.parameters(), lr=lr, lr_decay=1e-4, weight_decay=0.0)
@@ -128,7 +128,7 @@ def test_adagrad_loss_trajectory_follows_the_oracle(cuda_dev):
     xd = [x.cuda() for x in xs]
     ours, ref = [], []
     for it in range(steps):
-        out = [m(x) for x in xd]
+        out = m.forward_triplet(*xd)
         loss = crit.forward(*out)
         opt.zero_grad()
         loss.backward()
@@ -146,7 +146,7 @@ def test_adagrad_loss_trajectory_follows_the_oracle(cuda_dev):
         ref.append(oloss.item())
     dev = max(abs(a - b) / max(abs(b), 0.05) for a, b in zip(ours, ref))
     print("loss trajectory ours:", [round(v, 4) for v in ours], "\n              oracle:", [round(v, 4) for v in ref], f"\nmax rel dev {dev:.3e}")
-    assert abs(ours[0] - ref[0]) <= 2e-3 * max(ref[0], 0.05) and abs(ours[1] - ref[1]) <= 5e-3 * max(ref[1], 0.05)
-    assert ref[-1] < 0.8 * ref[0], "the oracle itself must learn on the fixed batch"
-    assert ours[-1] < 0.8 * ours[0]
-    assert dev < 0.15
+    assert abs(ours[0] - ref[0]) <= 3e-3 * max(ref[0], 0.05)
+    assert 0.0 < ref[-1] < 0.5 * ref[0], "the oracle itself must descend smoothly on the fixed batch"
+    assert ours[-1] < 0.5 * ours[0]
+    assert dev < 0.05
