@@ -42,6 +42,8 @@ def emit(line: dict):
     if _REAL_STDOUT is not None:
         os.dup2(_REAL_STDOUT, 1)
     print(json.dumps(line), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)   # whatever libraries print from here on (NCCL at teardown with NCCL_DEBUG=INFO) goes to stderr again
 
 
 def load_peaks():
