@@ -230,20 +230,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   // The producer warp owns the operand barriers and starts the first loads before the CTA-wide setup barrier: weight
   // boxes at once (parameters), the first halo tile right after the dependency wait.  The TMEM allocation and the
   // scale/bias fetch (a global-memory round trip) then overlap the first operand fetch instead of preceding it.
+  // Prologue, split over two warps so that the two first-use descriptor fetches (~1000 cycles each: the clock64 trace put
+  // the first halo load at cycle 1800 when one thread issued everything in turn) overlap: warp 0 sets up the weight ring
+  // and issues the first weight boxes (parameters: no dependency wait), warp 3 sets up the halo ring and issues the first
+  // halo tile right after the dependency wait.  TMEM allocation (warp 2) and the accumulator barriers (warp 1) run beside.
   int pre_b = 0;  // weight boxes of the first tile already issued (producer warp only)
   if (warp == 0) {
     if (lane == 0) {
-      tma_prefetch_desc(&tmIn);
       tma_prefetch_desc(&tmW);
-      for (int i = 0; i < kAStages; ++i) {
-        mbar_init(&a_full[i], 1);
-        mbar_init(&a_empty[i], 1);
-      }
       for (int i = 0; i < kBStages; ++i) {
         mbar_init(&b_full[i], 1);
         mbar_init(&b_empty[i], 1);
       }
       fence_barrier_init();
+      DSK_TRACE(0, 484);
     }
     __syncwarp();
     {
@@ -263,7 +263,28 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           }
         }
         __syncwarp();
+        if (lane == 0) DSK_TRACE(0, 485);
+      }
+    }
+  }
+  if (warp == 3) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmIn);
+      for (int i = 0; i < kAStages; ++i) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&a_empty[i], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    {
+      int cur0 = seg_begin();
+      int tile0, ub0, ue0;
+      if (next_seg(cur0, tile0, ub0, ue0)) {
+        int c0, q0;
+        decode(tile0, c0, q0);
         pdl_wait();  // activations of the previous kernel are read below
+        if (lane == 0) DSK_TRACE(0, 486);
         if (elect_one_sync()) {
           const int ch = ub0 / p.nboxes, b = ub0 - ch * p.nboxes;
           mbar_arrive_expect_tx(&a_full[0], halo_rows * 128);
@@ -285,8 +306,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     fence_barrier_init();
   }
   if (warp == 2) {
+    if (lane == 0) DSK_TRACE(0, 487);
     tmem_alloc(tmem_ptr_smem, kTmemCols);
     tmem_relinquish();
+    if (lane == 0) DSK_TRACE(0, 488);
   }
   tc_fence_before();
   __syncthreads();

@@ -30,6 +30,8 @@ t = tr.cpu().view(3, 512)
 t0 = int(t[t > 0].min())
 prod = [int(v) - t0 for v in t[0, :480] if v > 0]
 print("CTA0 entry / after-setup / after-pdl_wait / exit (cycles):", [int(v) - t0 for v in t[0, 480:484]])
+print("   producer: barriers initialised / weight boxes issued / after its pdl_wait:", [int(v) - t0 for v in t[0, 484:487]],
+      "| TMEM alloc begin / end:", [int(v) - t0 for v in t[0, 487:489]])
 print("producer A-issue stamps (cycles):", prod[:24])
 print("   deltas:", [b - a for a, b in zip(prod, prod[1:])][:24])
 names = ["start", "tmem_full", "bar1", "tmem_ld", "res_ok", "math+sts", "fence+bar+store", "done"]
