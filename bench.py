@@ -619,7 +619,8 @@ def bench_train(args, D):
     achieved = 3 * B * TRAIN_FLOP_PER_UTT / (ms * 1e-3) / 1e12     # per GPU
     rec = {"metric": "utterances/sec through the triplet training step (3 forwards + loss + backward + allreduce + Adagrad)",
            "value": utt_per_step / (ms * 1e-3), "unit": "utt/s", "n_gpus": world, "steps": K, "warmup": W,
-           "ms_per_step": ms, "windows": {"n": len(ws), "ms_per_step_min": min(ws) / K, "ms_per_step_max": max(ws) / K},
+           "ms_per_step": ms, "windows": {"n": len(ws), "ms_per_step_min": min(ws) / K, "ms_per_step_max": max(ws) / K,
+                                            "ms_per_step_each": [round(w / K, 4) for w in ws]},
            "higher_is_better": True, "scaling": "weak", "dtype": args.dtype,
            "config": {"workload": f"triplet training step, batch {B} triplets per GPU (anchor/pos/neg), synthetic 64x{T} fbank, "
                                   f"branch A (train_triplet.py:215-224), Adagrad lr 0.1 (BASELINE configs[{2 if world == 1 else 4}])",
