@@ -59,7 +59,7 @@ class TrainForwardFn(torch.autograd.Function):
         engine = ctx.engine
         saved = ctx.saved_tensors
         params = saved[1:]
-        grads = [torch.empty_like(p) for p in params]
+        grads = engine.grad_scratch(params)
         g = L.DskGrads()
         for i in range(L.NUM_CONV):
             g.conv_w[i] = grads[3 * i].data_ptr()
