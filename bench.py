@@ -421,8 +421,9 @@ def bench_infer(args, D):
     step_ms_prof = sum(sec_ms)
     peaks = load_peaks()
     achieved = B * CONV_TC_FLOP_PER_EMB / (conv_ms * 1e-3) / 1e12
-    total_timed_ms = sum(ws)
-    peak = peaks["tflops_sustained"] if (total_timed_ms > 2000 and peaks["tflops_sustained"]) else peaks["tflops_burst"]
+    # the conv chain is timed alone (one forward, two events): the burst figure of MEASURED_PEAKS is its denominator; the
+    # sustained figure belongs to the in-production rate, which is measured inside a long back-to-back run
+    peak = peaks["tflops_burst"]
     traffic, traffic_src = measured_traffic(B, T)
     # the production step keeps `lanes` forwards in flight, so launches of different forwards overlap: the in-production
     # rate charges the conv FLOPs with the WHOLE measured step (conv1 and the tail run under other forwards' convs)
@@ -437,8 +438,9 @@ def bench_infer(args, D):
         "share_of_step": share, "section_ms": {"conv1": sec_ms[0], "tensor_core_convs": sec_ms[1], "tail": sec_ms[2]},
         "per_launch_ms_event_bracketed": [round(x, 5) for x in per_launch_ms],
         "in_production": {"achieved": overlapped, "frac": overlapped / peak,
+                          "frac_of_sustained_peak": (overlapped / peaks["tflops_sustained"]) if peaks.get("tflops_sustained") else None,
                           "how": f"same FLOPs / measured ms_per_step ({args.lanes} forwards in flight; the whole step is charged to the convs)"},
-        "peak_source": peaks["source"] + (" sustained" if peak == peaks["tflops_sustained"] else " burst"),
+        "peak_source": peaks["source"] + " burst",
     }
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
