@@ -231,6 +231,31 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
   }
 }
+// clamp both 16-bit halves of a packed pair to [lo, hi] (lo / hi packed the same way).  Identical to clamping in fp32
+// before the pack when lo and hi are exactly representable: rounding is monotonic, and like fminf / fmaxf the packed
+// min / max return the non-NaN operand.
+template <bool BF16>
+__device__ __forceinline__ uint32_t clip2(uint32_t v, uint32_t lo, uint32_t hi) {
+  if constexpr (BF16) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&v);
+    x = __hmin2(__hmax2(x, *reinterpret_cast<__nv_bfloat162*>(&lo)), *reinterpret_cast<__nv_bfloat162*>(&hi));
+    return *reinterpret_cast<uint32_t*>(&x);
+  } else {
+    __half2 x = *reinterpret_cast<__half2*>(&v);
+    x = __hmin2(__hmax2(x, *reinterpret_cast<__half2*>(&lo)), *reinterpret_cast<__half2*>(&hi));
+    return *reinterpret_cast<uint32_t*>(&x);
+  }
+}
+// 16-byte shared-memory accesses through 32-bit shared-window addresses (no generic-address translation)
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 template <bool BF16>
 __device__ __forceinline__ float2 unpack2(uint32_t u) {
   if constexpr (BF16) {
