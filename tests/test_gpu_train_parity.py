@@ -65,7 +65,7 @@ def oracle_step(sd, xs, margin, masks, storage, f64):
 
 
 # (B, T, max grad rel-L2 against the mask-pinned storage-matched oracle, embedding rel)
-CASES = [(6, 160, 4e-3, 1.5e-3), (16, 48, 4e-3, 3e-3), (128, 160, 4e-3, 1.5e-3)]
+CASES = [(6, 160, 4e-3, 1e-3), (16, 48, 4e-3, 2e-3), (128, 160, 4e-3, 1e-3)]   # measured: 5.9e-4 / 9.9e-4 / 6.3e-4 and 2.5e-3 / 2.3e-3 / 2.3e-3
 
 
 @pytest.mark.parametrize("B,T,gtol,etol", CASES)
@@ -85,7 +85,7 @@ def test_fp16_step_matches_mask_pinned_oracle(cuda_dev, B, T, gtol, etol):
     print(f"B={B} T={T}: emb rel {erel:.2e}, loss {loss.item():.6f} vs {oloss.item():.6f}, clip-mask flips {flips}/{total}, "
           f"worst grad rel-L2 {worst[0]:.2e} ({worst[1]})")
     assert erel < etol
-    assert abs(loss.item() - oloss.item()) <= 2e-3 * max(abs(oloss.item()), 0.05)
+    assert abs(loss.item() - oloss.item()) <= 1e-3 * max(abs(oloss.item()), 0.05)      # measured 1.7e-4 - 2e-4 relative
     assert len(grads) == 38
     for k in grads:
         assert rel_l2(grads[k], ograds[k]) < gtol, (k, rel_l2(grads[k], ograds[k]))
@@ -150,3 +150,19 @@ def test_adagrad_loss_trajectory_follows_the_oracle(cuda_dev):
     assert 0.0 < ref[-1] < 0.5 * ref[0], "the oracle itself must descend smoothly on the fixed batch"
     assert ours[-1] < 0.5 * ours[0]
     assert dev < 0.05
+
+
+def test_train_mode_embeddings_vs_the_plain_fp32_oracle_at_config2(cuda_dev):
+    """BASELINE configs[2] shape (128 utterances per call, T = 160), train-mode BatchNorm, against the oracle WITHOUT any
+    storage matching or mask pinning: the plain fp32 reference arithmetic.  The north star's 1e-3 applies to this number."""
+    sd = O.make_state_dict(1, 16)
+    m = make_model(sd, "fp16", cuda_dev)
+    worst = 0.0
+    for seed in (20, 21):
+        x = O.make_input(128, 160, seed, 3.0)
+        with torch.no_grad():
+            e = m(x.cuda()).cpu()
+            ref = O.forward(sd, x, True, {})
+        worst = max(worst, float(((e - ref).norm(dim=1) / ref.norm(dim=1)).max()))
+    print(f"train-mode embeddings vs plain fp32 oracle at B=128, T=160: max rel {worst:.2e}")
+    assert worst < 1e-3
