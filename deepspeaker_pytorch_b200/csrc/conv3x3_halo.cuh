@@ -112,7 +112,8 @@ struct HaloPlan {
 //           the last tile) with the tensor pipe idle (clock64 traces, profiles/r02_trace_halo.txt).  With two CTAs per
 //           SM - two tiles of one layer, the early-launched CTA of the next kernel of the chain, or a CTA of another
 //           forward in flight - one CTA's set-up and epilogue run under the other's MMAs.  Weight boxes shrink to one
-//           tap (16 KB at 128 channels), the residual is read straight from L2 instead of through a prefetched tile.
+//           tap (16 KB at 128 channels).  MEASURED SLOWER (single-tap boxes are TMA-request-rate bound: conv chain
+//           0.216 -> 0.275 ms, profiles/r02_stream_k.md): opt-in through DSK_SMALL_CTA=1, kept for the record.
 template <int N_TILE, int EW = 8>
 struct HaloSmem {
   static constexpr bool kSmall = EW == 4;
@@ -143,7 +144,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 
 // tmIn : 2-D (C, positions) view of the padded input, box {64, 128 + 2W + 4}
 // tmW  : 3-D (cin, cout, 9 taps) packed weights, box {64, N_TILE, 3}
-// tmOut/tmRes : 2-D (C, positions) views of the padded output / residual, box {64, 128}
+// tmOut : 2-D (C, positions) view of the padded output, box {64, 128}   (tmRes: unused since the residual is read from
+//         global memory through HaloParams::res_ptr; kept in the signature)
 constexpr int kHaloThreads = 384;  // EW = 8: 4 control warps + 8 epilogue warps (two per scheduler)
 constexpr int halo_threads(int ew) { return 128 + 32 * ew; }
 
