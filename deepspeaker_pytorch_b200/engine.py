@@ -113,7 +113,7 @@ class Engine:
         L.check(self.lib.dsk_load_weights(self.handle, ctypes.byref(w), L.cur_stream()), "dsk_load_weights")
         self._versions = vs
 
-    def grad_scratch(self, params, slots: int = 6):
+    def grad_scratch(self, params, slots: int = 6, with_flat: bool = False):
         """Per-parameter gradient tensors for one backward, as views of a flat scratch buffer that is allocated once and
         rotated over ``slots`` buffers (a backward allocated 38 tensors per call: ~0.2 ms of host time per context, and
         the training step is host-sensitive - ~450 kernel launches per 7 ms of GPU work).  Safe to recycle: a slot is
@@ -131,9 +131,9 @@ class Engine:
                     off += (p.numel() + 3) // 4 * 4
                 self._gscratch.append((key, flat, views))
             self._gslot = 0
-        _, _, views = self._gscratch[self._gslot]
+        _, flat, views = self._gscratch[self._gslot]
         self._gslot = (self._gslot + 1) % len(self._gscratch)
-        return views
+        return (flat, views) if with_flat else views
 
     # -- forward ------------------------------------------------------------------------------------
     def forward(self, x, training):

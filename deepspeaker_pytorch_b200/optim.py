@@ -51,6 +51,7 @@ class FusedAdagrad:
             view.copy_(p.data)
             p.data = view                                               # parameters now live in the flat buffer
             p.grad = self.flat_grad[o:o + p.numel()].view_as(p)         # autograd accumulates in place into the view
+            p._dsk_bucket_grad = p.grad                                 # lets TripletForwardFn add into the bucket directly
         self.step_count = 0
         self.collectives = 0
         self._weighted = False

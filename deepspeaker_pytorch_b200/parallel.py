@@ -31,6 +31,7 @@ class GradBucket:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("all bucketed parameters must be fp32 on one device")
             p.grad = self.flat[off:off + p.numel()].view_as(p)   # autograd accumulates in place into the view
+            p._dsk_bucket_grad = p.grad                          # lets TripletForwardFn add into the bucket directly
             off += p.numel()
         self.collectives = 0
 

@@ -102,30 +102,76 @@ def forward_train(engine, x):
     return emb
 
 
-def forward_train_many(engine, xs):
-    """Several independent train-mode forwards of one step (the anchor / positive / negative calls of
-    train_triplet.py:215) IN FLIGHT TOGETHER: forward k runs on its own side stream, so the HBM-bound BatchNorm passes
-    of one call overlap the tensor-core convs of another, and - because autograd replays every node on the stream its
-    forward ran on - so do the three backwards.  Results are those of the sequential calls, bit for bit: batch
-    statistics are per call anyway, and the running-statistics updates are recorded per call and committed afterwards
-    in call order (``dsk_train_ctx_commit_stats``).  All side streams are joined before returning."""
-    module = engine.module_ref
-    engine.sync_weights(eval_mode=False)
-    engine.train_calls += 1
-    params = _train_params(module)
-    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+class TripletForwardFn(torch.autograd.Function):
+    """The K train-mode forwards of one step as ONE autograd node.  Forward: call k on side stream k.  Backward: the K
+    backward chains on the same K streams, each into its own flat gradient buffer, then ONE ordered sum of the flat
+    buffers on the caller's stream.  K separate nodes gave the same numbers, but autograd then summed the three
+    gradients of each of the 38 parameters itself: 114 small ``add`` launches at the end of every step, serial, after the
+    last backward kernel (profiles/r02_train_launches_ncu.md).  The sum here runs in the order autograd used (last
+    call first: (g_n + g_p) + g_a), so the gradients are the same bits as those of K sequential calls."""
+
+    @staticmethod
+    def forward(ctx, engine, k, *args):
+        xs, params = args[:k], args[k:]
+        outs, tctxs = _launch_many(engine, xs)
+        ctx.engine, ctx.k, ctx.params = engine, k, params
+        ctx.guards = [_CtxGuard(engine, t) for t in tctxs]
+        ctx.out_shape = outs[0].shape
+        ctx.save_for_backward(*xs, *params)  # the inputs must outlive the backward (conv1's weight gradient reads them)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grad_embs):
+        engine, k, params = ctx.engine, ctx.k, ctx.params
+        _ = ctx.saved_tensors                      # raises if a parameter was modified in place since the forward
+        dev = engine.device
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            flats, views = [], None
+            for ge, st, guard in zip(grad_embs, engine.side_streams, ctx.guards):
+                ge = (torch.zeros(ctx.out_shape, device=dev, dtype=torch.float32) if ge is None
+                      else ge.float().contiguous())
+                flat, views = engine.grad_scratch(params, with_flat=True)
+                g = L.DskGrads()
+                for i in range(L.NUM_CONV):
+                    g.conv_w[i] = views[3 * i].data_ptr()
+                    g.bn_gamma[i] = views[3 * i + 1].data_ptr()
+                    g.bn_beta[i] = views[3 * i + 2].data_ptr()
+                g.fc_w = views[-2].data_ptr()
+                g.fc_b = views[-1].data_ptr()
+                st.wait_stream(cur)                # grad_emb was produced on the caller's stream
+                with torch.cuda.stream(st):
+                    L.check(engine.lib.dsk_rescnn_backward(engine.handle, guard.tctx, ge.data_ptr(), ctypes.byref(g),
+                                                           L.cur_stream()), "dsk_rescnn_backward")
+                guard.consume()
+                flats.append(flat)
+            for st in engine.side_streams[:k]:
+                cur.wait_stream(st)                # also keeps every grad_emb alive long enough: it is freed on `cur`
+            acc = flats[-1]                        # `views` are the views of this buffer
+            for f in reversed(flats[:-1]):
+                acc.add_(f)
+            # parameters whose .grad is a view of an optimizer / data-parallel bucket (FusedAdagrad, GradBucket):
+            # accumulate into the bucket with one multi-tensor add instead of 38 AccumulateGrad nodes
+            if all(p.grad is not None and p.grad is getattr(p, "_dsk_bucket_grad", None) for p in params):
+                torch._foreach_add_([p.grad for p in params], list(views))
+                return (None, None) + (None,) * k + (None,) * len(params)
+        return (None, None) + (None,) * k + tuple(views)
+
+
+def _launch_many(engine, xs):
+    """Forward k of ``xs`` on side stream k, running-statistics updates deferred; joins the side streams.  Returns
+    (embeddings, library contexts)."""
     dev = engine.device
     cur = torch.cuda.current_stream(dev)
     while len(engine.side_streams) < len(xs):
         engine.side_streams.append(torch.cuda.Stream(dev))
-    xs = [x.contiguous().float() for x in xs]
     L.check(engine.lib.dsk_set_defer_running_stats(engine.handle, 1), "dsk_set_defer_running_stats")
     outs, ctxs = [], []
     try:
         for x, st in zip(xs, engine.side_streams):
             st.wait_stream(cur)                      # inputs (and the parameters) were produced on the caller's stream
             with torch.cuda.stream(st):
-                emb, tctx = _forward_one(engine, x, params, need_grad)
+                emb, tctx = _forward_one(engine, x, None, False)
             x.record_stream(st)
             outs.append(emb)
             ctxs.append(tctx)
@@ -134,6 +180,27 @@ def forward_train_many(engine, xs):
     for st, emb in zip(engine.side_streams, outs):
         cur.wait_stream(st)
         emb.record_stream(cur)
+    return outs, ctxs
+
+
+def forward_train_many(engine, xs):
+    """Several independent train-mode forwards of one step (the anchor / positive / negative calls of
+    train_triplet.py:215) IN FLIGHT TOGETHER: forward k runs on its own side stream, so the HBM-bound BatchNorm passes
+    of one call overlap the tensor-core convs of another, and so do the three backwards (``TripletForwardFn``).
+    Results are those of the sequential calls, bit for bit: batch statistics are per call anyway, the running-statistics
+    updates are recorded per call and committed afterwards in call order (``dsk_train_ctx_commit_stats``), and the
+    gradients are summed in autograd's order.  All side streams are joined before returning."""
+    module = engine.module_ref
+    engine.sync_weights(eval_mode=False)
+    engine.train_calls += 1
+    params = _train_params(module)
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    xs = [x.contiguous().float() for x in xs]
+    if need_grad:
+        outs = list(TripletForwardFn.apply(engine, len(xs), *xs, *params))
+        ctxs = [g.tctx for g in outs[0].grad_fn.guards]
+    else:
+        outs, ctxs = _launch_many(engine, xs)
     for tctx in ctxs:                                # momentum updates in call order, on the caller's stream
         L.check(engine.lib.dsk_train_ctx_commit_stats(engine.handle, tctx, L.cur_stream()), "dsk_train_ctx_commit_stats")
         if not need_grad:

@@ -264,6 +264,33 @@ def test_forward_triplet_is_bit_identical_to_three_sequential_calls(cuda_dev):
         assert torch.equal(ev[1], m(xs[1]))
 
 
+def test_forward_triplet_accumulates_into_an_optimizer_bucket_like_autograd(cuda_dev):
+    """With FusedAdagrad (or GradBucket) every p.grad is a view of one flat bucket; TripletForwardFn then adds its summed
+    gradients into the bucket with one multi-tensor add and returns no per-parameter gradients.  Must give the bits
+    autograd's own accumulation gives for three sequential calls - also on top of a non-zero bucket (two backwards
+    without zero_grad) and after the views were dropped (module.zero_grad() -> falls back to returning gradients)."""
+    sd = O.make_state_dict(6, 16)
+    xs = [O.make_input(10, 64, s, 3.0).cuda() for s in (41, 42, 43)]
+    res = []
+    for fused in (False, True):
+        m = make_model(sd, "fp16", cuda_dev)
+        opt = dsk.FusedAdagrad(m.parameters(), lr=1e-3)
+        opt.zero_grad()
+        for rep in range(2):                         # second backward accumulates on top of the first
+            outs = m.forward_triplet(*xs) if fused else (m(xs[0]), m(xs[1]), m(xs[2]))
+            dsk.TripletMarginLoss(0.1).forward(*outs).backward()
+        torch.cuda.synchronize()
+        assert all(p.grad is p._dsk_bucket_grad for p in opt.params)
+        res.append(opt.flat_grad.clone())
+        opt.step()
+        res.append(opt.flat_param.clone())
+    assert torch.equal(res[0], res[2]) and torch.equal(res[1], res[3])
+    assert res[0].abs().max() > 0
+    m.zero_grad()                                    # set_to_none: the bucket views are gone -> ordinary autograd path
+    dsk.TripletMarginLoss(0.1).forward(*m.forward_triplet(*xs)).backward()
+    assert sum(p.grad is not None for p in m.parameters()) == 38
+
+
 def test_train_step_helper_runs_both_branches_like_the_oracle(cuda_dev, golden_dir):
     """steps.train_step (train_triplet.py:208-299 restated with device-side selection) against the oracle's branch-B step
     on the reference golden's configuration, then a branch-A step through the same helper."""
