@@ -120,6 +120,7 @@ SIGNATURES = {
     "dsk_create": (c_int32, [POINTER(c_void_p), c_int32, c_int32]),
     "dsk_destroy": (c_int32, [c_void_p]),
     "dsk_load_weights": (c_int32, [c_void_p, POINTER(DskWeights), c_void_p]),
+    "dsk_load_weights_train": (c_int32, [c_void_p, POINTER(DskWeights), c_void_p]),
     "dsk_share_weights": (c_int32, [c_void_p, c_void_p]),
     "dsk_rescnn_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "dsk_rescnn_forward_train": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_void_p), c_void_p]),

@@ -179,6 +179,7 @@ struct dsk_handle_s {
   bool bf16 = false;
   int num_sms = 148;
   bool weights_loaded = false;
+  bool eval_packed = false;           // false after dsk_load_weights_train: only the training path's operand images are current
   int emb = 512;
   long weights_epoch = 0;             // bumped by every dsk_load_weights
   dsk_handle_s* src = nullptr;        // dsk_share_weights: the handle whose packed weights this one borrows
@@ -1062,7 +1063,14 @@ int32_t dsk_destroy(dsk_handle h) {
   return DSK_OK;
 }
 
-int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
+namespace {
+int load_weights_impl(dsk_handle h, const dsk_weights* w, void* stream, bool train_only);
+}
+int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) { return load_weights_impl(h, w, stream, false); }
+int32_t dsk_load_weights_train(dsk_handle h, const dsk_weights* w, void* stream) { return load_weights_impl(h, w, stream, true); }
+
+namespace {
+int load_weights_impl(dsk_handle h, const dsk_weights* w, void* stream, bool train_only) {
   int rc = check_handle(h);
   if (rc) return rc;
   if (!w) return fail(DSK_ERR_INVALID, "dsk_load_weights: null weights");
@@ -1076,12 +1084,38 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
   h->plans.clear();
   h->host_affine_valid = false;
   h->emb = w->embedding_size;
+  h->eval_packed = !train_only;
+  dsk::PackTrainTable tbl{};
+  int nblk = 0;
   for (int i = 0; i < DSK_NUM_CONV; ++i) {
     const LayerCfg c = layer_cfg(i);
     const int taps = c.ksize * c.ksize;
     const long n = static_cast<long>(c.cout) * c.cin * taps;
     if (!w->conv_w[i] || !w->bn_gamma[i] || !w->bn_beta[i] || !w->bn_running_mean[i] || !w->bn_running_var[i])
       return fail(DSK_ERR_INVALID, "dsk_load_weights: null parameter pointer for conv/bn %d", i);
+    if (train_only) {
+      // the training path reads only wpk / wpk_dgrad / conv1_w / fc_wq: one table-driven launch below
+      tbl.w[i] = w->conv_w[i];
+      if (i == 0) {
+        if (!h->conv1_w) {
+          rc = dev_alloc(&h->conv1_w, 64 * 25);
+          if (rc) return rc;
+        }
+        tbl.conv1_dst = h->conv1_w;
+        continue;
+      }
+      if (!h->wpk[i]) {
+        CUDA_TRY(cudaMalloc(&h->wpk[i], n * 2));
+        CUDA_TRY(cudaMalloc(&h->wpk_dgrad[i], n * 2));
+      }
+      tbl.fwd[i] = static_cast<uint16_t*>(h->wpk[i]);
+      tbl.dgrad[i] = static_cast<uint16_t*>(h->wpk_dgrad[i]);
+      tbl.cout[i] = c.cout, tbl.cin[i] = c.cin, tbl.taps[i] = taps, tbl.rotate[i] = c.stride == 1;
+      tbl.first_block[i] = nblk;
+      nblk += (c.cout / dsk::kPackCo) * (c.cin / dsk::kPackCi);
+      tbl.first_block[i + 1] = nblk;
+      continue;
+    }
     if (!h->scale[i]) {
       rc = dev_alloc(&h->scale[i], c.cout);
       if (rc) return rc;
@@ -1133,6 +1167,11 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
       KERNEL_CHECK();
     }
   }
+  if (train_only) {
+    if (h->bf16) dsk::pack_train_weights_kernel<true><<<nblk + 1, 256, 0, s>>>(tbl);
+    else dsk::pack_train_weights_kernel<false><<<nblk + 1, 256, 0, s>>>(tbl);
+    KERNEL_CHECK();
+  }
   if (!w->fc_w || !w->fc_b) return fail(DSK_ERR_INVALID, "dsk_load_weights: null fc pointer");
   if (!h->fc_wq) {
     rc = dev_alloc(&h->fc_wq, static_cast<size_t>(h->emb) * 2048);
@@ -1145,6 +1184,7 @@ int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream) {
   h->weights_loaded = true;
   return DSK_OK;
 }
+}  // namespace
 
 int32_t dsk_share_weights(dsk_handle h, dsk_handle src) {
   int rc = check_handle(h);
@@ -1181,6 +1221,7 @@ void adopt_shared_weights(dsk_handle h) {
   h->w = s->w;
   h->emb = s->emb;
   h->weights_loaded = s->weights_loaded;
+  h->eval_packed = s->eval_packed;
   h->plans.clear();
   h->host_affine_valid = false;
   h->seen_epoch = s->weights_epoch;
@@ -1372,6 +1413,9 @@ int32_t dsk_rescnn_forward(dsk_handle h, const float* x, int32_t B, int32_t T, f
   if (rc) return rc;
   adopt_shared_weights(h);
   if (!h->weights_loaded) return fail(DSK_ERR_STATE, "dsk_rescnn_forward: call dsk_load_weights first");
+  if (!h->eval_packed)
+    return fail(DSK_ERR_STATE, "dsk_rescnn_forward: the weights were loaded with dsk_load_weights_train (training operand "
+                               "images only); call dsk_load_weights before an eval forward");
   if (!x || !emb || B <= 0) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: bad arguments");
   if (T < 16 || T % 16) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: T must be a positive multiple of 16 (got %d)", T);
   if (mode != DSK_EVAL) return fail(DSK_ERR_INVALID, "dsk_rescnn_forward: use dsk_rescnn_forward_train for batch-statistics BN");

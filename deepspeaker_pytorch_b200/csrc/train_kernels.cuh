@@ -570,4 +570,54 @@ __global__ void loss_scale_kernel(const float* __restrict__ g, long n, float fix
   }
 }
 
+// ---- weight repack of a training step: ONE launch for all eleven tensor-core convs -----------------------------------
+// A training step changes every parameter, so the 16-bit operand images are rebuilt once per step, on the caller's
+// stream, before the three forwards fork: 44 small launches with strided 4-byte gathers (0.3 ms of a 6.4 ms step,
+// profiles/r02_train_launches_ncu.md).  Here a block owns a 16 (cout) x 32 (cin) x taps tile of one layer: it reads the
+// OIHW fp32 rows contiguously, keeps the rounded 16-bit values in shared memory and writes both images the training path
+// reads - [tap][cout][cin] for the forward / weight-gradient convs and [tap'][cin][cout] (filter turned by 180 degrees
+// for stride 1) for the data gradient - in 64- and 32-byte runs.  The last block copies conv1's 64x25 fp32 filter.
+struct PackTrainTable {
+  const float* w[12];
+  uint16_t* fwd[12];
+  uint16_t* dgrad[12];
+  int cout[12], cin[12], taps[12], rotate[12];
+  int first_block[13];   // first_block[i] .. first_block[i+1]: the blocks of layer i (i = 1..11); [12] = conv1 block
+  float* conv1_dst;
+};
+constexpr int kPackCo = 16, kPackCi = 32;
+template <bool BF16>
+__global__ void __launch_bounds__(256) pack_train_weights_kernel(const PackTrainTable t) {
+  __shared__ uint16_t sm[kPackCo][kPackCi * 25 + 2];
+  const int b = blockIdx.x;
+  if (b >= t.first_block[12]) {
+    for (int i = threadIdx.x; i < 64 * 25; i += blockDim.x) t.conv1_dst[i] = t.w[0][i];
+    return;
+  }
+  int l = 1;
+  while (b >= t.first_block[l + 1]) ++l;
+  const int cout = t.cout[l], cin = t.cin[l], taps = t.taps[l];
+  const int lb = b - t.first_block[l];
+  const int ci_tiles = cin / kPackCi;
+  const int co0 = (lb / ci_tiles) * kPackCo, ci0 = (lb % ci_tiles) * kPackCi;
+  const int row = kPackCi * taps;                     // contiguous floats of one cout row of the tile
+  const float* __restrict__ w = t.w[l];
+  for (int i = threadIdx.x; i < kPackCo * row; i += blockDim.x) {
+    const int r = i / row, j = i - r * row;
+    sm[r][j] = to16<BF16>(w[(static_cast<long>(co0 + r) * cin + ci0) * taps + j]);
+  }
+  __syncthreads();
+  uint16_t* __restrict__ of = t.fwd[l];
+  for (int i = threadIdx.x; i < taps * kPackCo * kPackCi; i += blockDim.x) {
+    const int ci = i % kPackCi, r = (i / kPackCi) % kPackCo, tap = i / (kPackCi * kPackCo);
+    of[(static_cast<long>(tap) * cout + co0 + r) * cin + ci0 + ci] = sm[r][ci * taps + tap];
+  }
+  uint16_t* __restrict__ od = t.dgrad[l];
+  const int rot = t.rotate[l];
+  for (int i = threadIdx.x; i < taps * kPackCo * kPackCi; i += blockDim.x) {
+    const int r = i % kPackCo, ci = (i / kPackCo) % kPackCi, tap = i / (kPackCi * kPackCo);
+    od[(static_cast<long>(tap) * cin + ci0 + ci) * cout + co0 + r] = sm[r][ci * taps + (rot ? taps - 1 - tap : tap)];
+  }
+}
+
 }  // namespace dsk

@@ -110,7 +110,10 @@ class Engine:
         w.fc_b = _f32c(m.model.fc.bias.data).data_ptr()
         w.embedding_size = m.embedding_size
         self._wstruct = w
-        L.check(self.lib.dsk_load_weights(self.handle, ctypes.byref(w), L.cur_stream()), "dsk_load_weights")
+        if eval_mode:
+            L.check(self.lib.dsk_load_weights(self.handle, ctypes.byref(w), L.cur_stream()), "dsk_load_weights")
+        else:   # once per training step: only the operand images the training path reads, in one launch
+            L.check(self.lib.dsk_load_weights_train(self.handle, ctypes.byref(w), L.cur_stream()), "dsk_load_weights_train")
         self._versions = vs
 
     def grad_scratch(self, params, slots: int = 6, with_flat: bool = False):

@@ -80,6 +80,12 @@ int32_t dsk_destroy(dsk_handle h);
 /* Repack conv weights to [tap][cout][cin] 16-bit, fold eval BatchNorm to scale/bias, reorder fc.
  * Must be called after every parameter update (the Python shim tracks parameter versions). */
 int32_t dsk_load_weights(dsk_handle h, const dsk_weights* w, void* stream);
+/* The same for a handle that is about to TRAIN (every optimizer step changes every parameter, so this runs once per
+ * step, before the forwards): rebuilds only what dsk_rescnn_forward_train / dsk_rescnn_backward read - the forward and
+ * data-gradient operand images of the eleven tensor-core convs (one kernel launch), conv1's filter and the reordered fc
+ * weight - and skips the eval-only work (BatchNorm folding, conv1's split image, the plane-major 5x5 images).
+ * dsk_rescnn_forward (eval) then fails with DSK_ERR_STATE until dsk_load_weights is called again. */
+int32_t dsk_load_weights_train(dsk_handle h, const dsk_weights* w, void* stream);
 /* Serving with several forwards in flight (one handle + activation workspace per compute stream): `h` borrows the
  * packed weights / folded BN of `src` instead of holding its own copy, so all lanes read one 21 MB weight image (it
  * has to stay L2-resident: the convs re-read it per tile).  `h` follows later dsk_load_weights(src) calls at its next

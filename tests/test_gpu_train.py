@@ -291,6 +291,42 @@ def test_forward_triplet_accumulates_into_an_optimizer_bucket_like_autograd(cuda
     assert sum(p.grad is not None for p in m.parameters()) == 38
 
 
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+def test_training_weight_repack_writes_the_same_operand_images(cuda_dev, dt):
+    """dsk_load_weights_train (one table-driven launch per step, only the images the training path reads) against the full
+    dsk_load_weights (per-layer pack kernels): a train-mode forward + backward must give the same bits with either, and an
+    eval forward on a handle that only holds the training images is refused."""
+    import ctypes
+    from deepspeaker_pytorch_b200 import _lib as L
+    sd = O.make_state_dict(8, 16)
+    xs = [O.make_input(6, 64, s, 3.0).cuda() for s in (51, 52, 53)]
+    m = make_model(sd, dt, cuda_dev)
+
+    def step():
+        outs = m.forward_triplet(*xs)
+        m.zero_grad()
+        dsk.TripletMarginLoss(0.1).forward(*outs).backward()
+        torch.cuda.synchronize()
+        return [o.detach().clone() for o in outs], {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    o_train, g_train = step()                                   # sync_weights(train) -> dsk_load_weights_train
+    eng = m._engine
+    x0, emb = xs[0].contiguous(), torch.empty(6, 512, device="cuda")
+    rc = eng.lib.dsk_rescnn_forward(eng.handle, x0.data_ptr(), 6, 64, emb.data_ptr(), 0, L.cur_stream())
+    assert rc != 0 and b"dsk_load_weights_train" in eng.lib.dsk_last_error()
+    L.check(eng.lib.dsk_load_weights(eng.handle, ctypes.byref(eng._wstruct), L.cur_stream()), "dsk_load_weights")
+    o_full, g_full = step()                                     # parameter versions unchanged: no repack in between
+    for a, b in zip(o_train, o_full):
+        assert torch.equal(a, b)
+    assert len(g_train) == 38
+    for k in g_train:
+        assert torch.equal(g_train[k], g_full[k]), k
+    m.eval()                                                    # the shim reloads everything for an eval forward
+    with torch.no_grad():
+        e = m(xs[0])
+    assert torch.isfinite(e).all() and abs(float(e.norm(dim=1).mean()) - 10.0) < 1e-3
+
+
 def test_train_step_helper_runs_both_branches_like_the_oracle(cuda_dev, golden_dir):
     """steps.train_step (train_triplet.py:208-299 restated with device-side selection) against the oracle's branch-B step
     on the reference golden's configuration, then a branch-A step through the same helper."""
