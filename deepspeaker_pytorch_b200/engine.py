@@ -48,6 +48,7 @@ class Engine:
         self.train_calls = 0  # train-mode forwards update BN running stats through raw pointers
         self.side_streams = []  # forward_train_many: one stream per forward in flight
         self._gscratch, self._gslot = [], 0
+        self.bucket_accumulations = 0  # backwards that added their gradients straight into an optimizer bucket
         self.share_from = share_from
         if share_from is not None:
             L.check(self.lib.dsk_share_weights(self.handle, share_from.handle), "dsk_share_weights")

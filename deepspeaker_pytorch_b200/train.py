@@ -152,10 +152,23 @@ class TripletForwardFn(torch.autograd.Function):
                 acc.add_(f)
             # parameters whose .grad is a view of an optimizer / data-parallel bucket (FusedAdagrad, GradBucket):
             # accumulate into the bucket with one multi-tensor add instead of 38 AccumulateGrad nodes
-            if all(p.grad is not None and p.grad is getattr(p, "_dsk_bucket_grad", None) for p in params):
+            if (all(p.grad is not None and p.grad is getattr(p, "_dsk_bucket_grad", None) for p in params)
+                    and _engine_accumulates_into(ctx, params)):
                 torch._foreach_add_([p.grad for p in params], list(views))
+                engine.bucket_accumulations += 1
                 return (None, None) + (None,) * k + (None,) * len(params)
         return (None, None) + (None,) * k + tuple(views)
+
+
+def _engine_accumulates_into(node, params):
+    """True when the running backward will accumulate this node's parameter gradients into ``p.grad`` (``loss.backward()``),
+    False when it captures them instead (``torch.autograd.grad``: the AccumulateGrad nodes are not executed and the query
+    raises) - then the gradients must be returned to autograd, not added into the bucket."""
+    try:
+        acc = {id(fn.variable): fn for fn, _ in node.next_functions if fn is not None and hasattr(fn, "variable")}
+        return all(id(p) in acc and torch._C._will_engine_execute_node(acc[id(p)]) for p in params)
+    except Exception:
+        return False
 
 
 def _launch_many(engine, xs):

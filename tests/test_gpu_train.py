@@ -281,11 +281,18 @@ def test_forward_triplet_accumulates_into_an_optimizer_bucket_like_autograd(cuda
             dsk.TripletMarginLoss(0.1).forward(*outs).backward()
         torch.cuda.synchronize()
         assert all(p.grad is p._dsk_bucket_grad for p in opt.params)
+        assert m._engine.bucket_accumulations == (2 if fused else 0)
         res.append(opt.flat_grad.clone())
         opt.step()
         res.append(opt.flat_param.clone())
     assert torch.equal(res[0], res[2]) and torch.equal(res[1], res[3])
     assert res[0].abs().max() > 0
+    # torch.autograd.grad captures gradients instead of accumulating them: the bucket must stay untouched
+    before = opt.flat_grad.clone()
+    path = [p for p in opt.params if p.grad is not None][:38]
+    got = torch.autograd.grad(dsk.TripletMarginLoss(0.1).forward(*m.forward_triplet(*xs)), path, allow_unused=True)
+    assert torch.equal(opt.flat_grad, before) and sum(g is not None and bool(g.abs().max() > 0) for g in got) >= 36
+    assert m._engine.bucket_accumulations == 2
     m.zero_grad()                                    # set_to_none: the bucket views are gone -> ordinary autograd path
     dsk.TripletMarginLoss(0.1).forward(*m.forward_triplet(*xs)).backward()
     assert sum(p.grad is not None for p in m.parameters()) == 38
