@@ -93,3 +93,33 @@ def test_conv1_split_operand_arithmetic():
         assert np.abs(got - ref).max() / scale < bound
         plain = xh.astype(np.float64) @ wh.astype(np.float64)                # what a single 16-bit product would give
         assert np.abs(plain - ref).max() / scale > 20 * bound
+
+
+def test_bucket_accumulation_is_only_taken_when_autograd_accumulates():
+    """train._engine_accumulates_into decides, inside a backward, whether the gradients of the path's parameters may be added
+    straight into the optimizer bucket: yes under loss.backward() (the AccumulateGrad nodes of the leaves will run), no under
+    torch.autograd.grad (gradients are captured and must be returned)."""
+    from deepspeaker_pytorch_b200 import train as T
+
+    seen = []
+
+    class Scale(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, tag, x, w, b):          # a non-tensor argument first, like TripletForwardFn(engine, k, ...)
+            ctx.params = (w, b)
+            return x * w + b
+
+        @staticmethod
+        def backward(ctx, g):
+            seen.append(T._engine_accumulates_into(ctx, ctx.params))
+            return None, None, g, g
+
+    w = torch.ones(3, requires_grad=True)
+    b = torch.zeros(3, requires_grad=True)
+    x = torch.arange(3.0)
+    Scale.apply("t", x, w, b).sum().backward()
+    torch.autograd.grad(Scale.apply("t", x, w, b).sum(), [w, b])
+    Scale.apply("t", x, w, b).sum().backward(inputs=[w, b])
+    other = torch.ones(3, requires_grad=True)
+    seen.append(T._engine_accumulates_into(Scale.apply("t", x, w, b).grad_fn, (w, other)))   # not a parameter of the node
+    assert seen == [True, False, True, False]
